@@ -1,0 +1,41 @@
+"""Shared test helpers: golden-file loading and the parity norms of SURVEY 8c."""
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+FEATURE_CASES = ["kat_path", "kat_path_loops", "cora_noloop", "cora_loops", "pubmed_noloop",
+                 "cora_k0", "cora_k1", "cora_k6_s04", "directed_weighted", "cora_wide8",
+                 "small_wide130"]
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    n = int(z["n"])
+    adj = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+    k = int(z["k"])
+    return dict(name=name, n=n, k=k, s=float(z["s"]), adj=adj,
+                lt=sp.csr_matrix((z["lt_data"], z["lt_indices"], z["lt_indptr"]), shape=(n, n)),
+                X0=z["X0"], T=[z[f"T{i}"] for i in range(k + 1)], S=z["S"], H=z["H"],
+                custom_x0=bool(z["custom_x0"]))
+
+
+def rel_max_err(got, ref):
+    """||got-ref||_inf / ||ref||_inf (the per-order parity norm)."""
+    ref = np.asarray(ref, dtype=np.float64)
+    got = np.asarray(got, dtype=np.float64)
+    denom = np.abs(ref).max()
+    if denom == 0:
+        return float(np.abs(got).max())
+    return float(np.abs(got - ref).max() / denom)
+
+
+def elementwise_ok(got, ref, tol=1e-5):
+    """abs(delta) <= tol * max(|ref|, 1e-3 * ||ref||_inf) for every element."""
+    ref = np.asarray(ref, dtype=np.float64)
+    got = np.asarray(got, dtype=np.float64)
+    floor = 1e-3 * np.abs(ref).max()
+    return bool(np.all(np.abs(got - ref) <= tol * np.maximum(np.abs(ref), floor) + 1e-30))
