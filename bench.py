@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the Chebyshev graph-wavelet feature path (BASELINE.json metric:
+"Chebyshev-wavelet nnz*K*F/s & HBM GB/s at 1/2/4/8 B200 vs ref CPU").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload reddit|arxiv|physics|pubmed|cora] [--f F] [--order K] [--scales S]
+
+One "step" = one pass of the hot path over one synthetic graph of the named
+shape: K fused Chebyshev orders (CSR SpMM over the implicit scaled Laplacian +
+recurrence + scale accumulation + L1 normalisation).  Default workload: the
+Reddit shape (232,965 nodes, 114.6 M stored entries) with the reference's
+defaults K=3, S=1 (s=0.8), F=1 (X0 = log1p(degree)) - the largest named
+configuration; it fits one B200 and is the only one whose CSR streams from HBM.
+
+Prints ONE JSON line (see README/DESIGN.md for the keys).  `value` is timed with
+the graph resident in HBM; `e2e` is the same metric through the host-buffer
+entry (pinned host CSR -> H2D -> degree pass -> orders -> D2H of the features).
+`--impl reference` times the CPU oracle port of the reference's scipy path
+(the reference itself is pure Python + scipy and is not present on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "chebyshev_wavelet_nnz_k_f_per_s"
+UNIT = "nnz*K*F/s"
+DEFAULT_F = {"reddit": 1, "arxiv": 128, "physics": 1, "pubmed": 1, "cora": 1}
+CPU_RATE_GUESS = 6.4e6      # nnz*K*F/s of the reference path on one core
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reddit", choices=sorted(DEFAULT_F))
+    ap.add_argument("--f", type=int, default=None, help="feature columns of X0 (default: per workload)")
+    ap.add_argument("--order", type=int, default=3, help="Chebyshev order K")
+    ap.add_argument("--scales", type=int, default=1, help="number of wavelet scales S")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def scale_list(n_scales):
+    base = [0.8, 0.4, 1.6, 3.2, 0.2, 6.4, 0.1, 12.8]
+    return base[0] if n_scales == 1 else base[:n_scales]
+
+
+def algorithmic_bytes(n, nnz, f, k_max, n_scales):
+    """Compulsory-traffic model B_k of SURVEY 8d (int32 indices, fp32 data,
+    binary adjacency) for each order k = 1..K."""
+    out = []
+    for k in range(1, k_max + 1):
+        t_terms = 1 + (1 if k >= 2 else 0) + (1 if k < k_max else 0)
+        acc = 1 if k == 1 else 2
+        out.append(4 * nnz + 4 * (n + 1) + 4 * n + 4 * n * f * t_terms + 4 * n_scales * n * f * acc)
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock / throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def poll(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "hw_power_brake_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        for name, bit in names.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag:
+            try:
+                self.poll()
+            except Exception:
+                break
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------------- #
+# CPU arm: the oracle port of the reference's scipy path                        #
+# --------------------------------------------------------------------------- #
+def cpu_sample_graph(workload, target_seconds, k_max, f, gen_device):
+    """A bounded sample of the workload: the same generator at a reduced scale
+    (nodes and entries shrunk together, same mean degree)."""
+    import scipy.sparse as sp
+    from efficient_gnn_b200 import synth
+    sh = synth.SHAPES[workload]
+    want_nnz = CPU_RATE_GUESS * target_seconds / max(1, k_max)      # F enters through the recurrence only
+    scale = float(min(1.0, max(2e-3, want_nnz / sh.nnz)))
+    rp, ci, n = synth.synth_csr(workload, self_loops=True, device=gen_device, scale=scale)
+    rp, ci = rp.cpu().numpy(), ci.cpu().numpy()
+    adj = sp.csr_matrix((np.ones(ci.size, np.float32), ci, rp), shape=(n, n))
+    return adj, scale
+
+
+def time_oracle(adj, k_max, scales, f, repeats=1):
+    from oracle import wats_oracle as orc
+    x0 = None
+    if f > 1:
+        x0 = np.random.default_rng(3).standard_normal((adj.shape[0], f)).astype(np.float32)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.wavelet_features(adj, k=k_max, s=scales, x0=x0)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the CPU implementation of the path (oracle port of
+    calibration/WATS.py:39-74 over scipy, single-threaded like the reference)
+    on a bounded sample per step."""
+    if rank != 0:
+        return
+    f = args.f or DEFAULT_F[args.workload]
+    scales = scale_list(args.scales)
+    total = max(1, args.steps + args.warmup)
+    per_step = min(20.0, max(0.5, 150.0 / total))
+    adj, scale = cpu_sample_graph(args.workload, per_step, args.order, f, "cpu")
+    for _ in range(args.warmup):
+        time_oracle(adj, args.order, scales, f)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        time_oracle(adj, args.order, scales, f)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = adj.nnz * args.order * f / dt
+    sample = (f"{args.workload}-shape generator at scale {scale:.4f} (N={adj.shape[0]}, nnz={adj.nnz}), "
+              f"K={args.order}, S={args.scales}, F={f}; one full path per step")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}-shape", "k": args.order, "scales": args.scales, "f": f,
+                   "sample_scale": scale, "n": int(adj.shape[0]), "nnz": int(adj.nnz)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- #
+# GPU arm                                                                       #
+# --------------------------------------------------------------------------- #
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+    import efficient_gnn_b200 as egnn
+    from efficient_gnn_b200 import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    f = args.f or DEFAULT_F[args.workload]
+    k_max, n_scales = args.order, args.scales
+    scales = scale_list(n_scales)
+    sh = synth.SHAPES[args.workload]
+
+    if world > 1:
+        from efficient_gnn_b200 import sharded
+        return sharded.bench_entry(args, rank, local_rank, world, METRIC, UNIT, algorithmic_bytes,
+                                   ClockSampler, physical_gpu_index, scale_list)
+
+    # synthetic graph of the named shape, generated directly in HBM
+    rp, ci, n = synth.synth_csr(args.workload, self_loops=True, device=dev)
+    graph = egnn.CsrGraph(rp, ci, None, n)
+    nnz = graph.nnz
+    if f == 1:
+        x0 = None                                  # reference default: log1p(degree), produced by the degree pass
+    else:
+        x0 = torch.randn(n, f, device=dev, generator=torch.Generator(device=dev).manual_seed(sh.seed))
+    work = float(nnz) * k_max * f
+
+    def step(events=None):
+        return egnn.graph_wavelet_features(graph, k=k_max, s=scales, X0=x0, _order_events=events)
+
+    # per-order CUDA events (recorded by the library on the launching stream)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * k_max)] for _ in range(args.steps)]
+    for row in ev:                                 # materialise the handles
+        for e in row:
+            e.record()
+    torch.cuda.synchronize()
+    import ctypes as C
+    ev_arrays = [(C.c_void_p * (2 * k_max))(*[e.cuda_event for e in row]) for row in ev]
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    for i in range(args.steps):
+        step(ev_arrays[i])
+    stop.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join()
+    ms_per_step = start.elapsed_time(stop) / args.steps
+    value = work / (ms_per_step * 1e-3)
+
+    order_ms = np.array([[row[2 * j].elapsed_time(row[2 * j + 1]) for j in range(k_max)] for row in ev])
+    avg_launch_ms = float(order_ms.mean())
+    b_k = algorithmic_bytes(n, nnz, f, k_max, n_scales)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = (sum(b_k) / k_max) / (avg_launch_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"{args.workload}_f{f}_k{k_max}_s{n_scales}")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "cheb_order_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": sum(b_k) / k_max, "avg_launch_ms": avg_launch_ms,
+                "per_order_ms": [float(v) for v in order_ms.mean(axis=0)],
+                "order_kernel_share_of_step": float(order_ms.sum(axis=1).mean() / ms_per_step)}
+
+    # end to end through the host-buffer entry: pinned CSR -> device -> features -> host
+    e2e = None
+    if not args.no_e2e:
+        rp_h = graph.rowptr.cpu().pin_memory()
+        ci_h = graph.colidx.cpu().pin_memory()
+        x0_h = None if x0 is None else x0.cpu().pin_memory()
+        out_h = torch.empty((n, n_scales * f), dtype=torch.float32).pin_memory()
+        h2d = rp_h.numel() * 4 + ci_h.numel() * 4 + (0 if x0_h is None else x0_h.numel() * 4)
+        d2h = out_h.numel() * 4
+
+        def e2e_step():
+            g = egnn.CsrGraph.from_host_csr(rp_h, ci_h, None, n, device=dev)
+            xx = None if x0_h is None else x0_h.to(dev, non_blocking=True)
+            feats = egnn.graph_wavelet_features(g, k=k_max, s=scales, X0=xx)
+            out_h.copy_(feats, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        e_steps = max(3, min(args.steps, 20))
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e_dt = (time.perf_counter() - t0) / e_steps
+        e2e = {"value": work / e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e_dt * 1e3, "steps": e_steps,
+               "entry": "CsrGraph.from_host_csr + graph_wavelet_features (pinned host CSR in, host features out)"}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        adj, scale = cpu_sample_graph(args.workload, 12.0, k_max, f, dev)
+        t_cpu = time_oracle(adj, k_max, scales, f)
+        cpu_baseline = {"value": adj.nnz * k_max * f / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                        "host_cores": os.cpu_count(), "seconds": t_cpu,
+                        "sample": (f"{args.workload}-shape generator at scale {scale:.4f} (N={adj.shape[0]}, "
+                                   f"nnz={adj.nnz}), same K/S/F; oracle port of calibration/WATS.py:39-74 "
+                                   "(scipy, single-threaded like the reference), one run")}
+
+    launches_per_step = k_max + (1 if f <= 4 else 0) + (1 if f > 128 else 0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}-shape", "n": n, "nnz": nnz, "k": k_max, "scales": n_scales, "f": f,
+                   "self_loops": True, "parallelism": "1 GPU", "l2_policy": (
+                       "inputs larger than L2 (CSR %.0f MB vs 126 MB L2), no flush" % (4 * nnz / 1e6)
+                       if 4 * nnz > 126e6 else "inputs fit in L2: latency-bound configuration, no flush")},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": sampler.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

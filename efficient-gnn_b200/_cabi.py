@@ -1,0 +1,92 @@
+"""ctypes binding of ``lib/libegnn_b200.so`` (C ABI declared in include/egnn_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or the
+device is not sm_100, every entry point raises.  Build it with
+``python -c "import __graft_entry__ as g; g.build()"`` or
+``efficient-gnn_b200/csrc/build.sh``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libegnn_b200.so")
+ABI_VERSION = 1
+
+# every symbol include/egnn_b200.h declares: name -> (restype, argtypes)
+_P, _I32, _I64, _F32, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+SYMBOLS = {
+    "egnn_abi_version": (C.c_int, []),
+    "egnn_last_error": (C.c_char_p, []),
+    "egnn_device_info": (C.c_int, [_P, _P, _P]),
+    "egnn_dense_to_csr_count": (C.c_int, [_P, _I64, _I64, _P, _P, _P]),
+    "egnn_dense_to_csr_fill": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P]),
+    "egnn_graph_prep": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "egnn_patch_degrees": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _P, _P, _P, _P]),
+    "egnn_cheb_workspace_bytes": (_SZ, [_I64, _I32]),
+    "egnn_cheb_wavelet": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, _F32, _F32,
+                                    _P, _P, _I32, _P, _P, _P, _I32, _P, _SZ, _P, _P]),
+    "egnn_cheb_order_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                          _I64, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _P, _F32, _F32,
+                                          _I32, _I32, _P]),
+}
+
+
+class EgnnError(RuntimeError):
+    """A non-zero status from libegnn_b200 (message from egnn_last_error)."""
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise if it is absent (no CPU fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise EgnnError(
+                f"{LIB_PATH} not found: the CUDA extension is required (there is no CPU "
+                "fallback). Build it with efficient-gnn_b200/csrc/build.sh")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        got = lib.egnn_abi_version()
+        if got != ABI_VERSION:
+            raise EgnnError(f"libegnn_b200 ABI {got} != binding ABI {ABI_VERSION}; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().egnn_last_error().decode("utf-8", "replace")
+        raise EgnnError(f"{what or 'libegnn_b200'} failed (status {rc}): {msg}")
+
+
+def ptr(t):
+    """Device (or host) address of a tensor, or NULL for None."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def host_array(ctype, values):
+    arr = (ctype * max(1, len(values)))(*values)
+    return arr
+
+
+def require_device():
+    """Fail loudly unless a B200-class device is current."""
+    import torch
+    if not torch.cuda.is_available():
+        raise EgnnError("efficient-gnn-b200 needs a CUDA device (sm_100a); there is no CPU path")
+    sm, major, minor = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    check(load().egnn_device_info(C.byref(sm), C.byref(major), C.byref(minor)), "egnn_device_info")
+    return sm.value, major.value, minor.value

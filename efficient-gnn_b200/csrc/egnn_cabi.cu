@@ -1,0 +1,369 @@
+// extern "C" surface of libegnn_b200.so (declared in include/egnn_b200.h).
+// Host-side driver logic only: argument checks, kernel selection, launches on
+// the caller's stream.  No allocation, no synchronisation, no global state.
+#include <stdarg.h>
+
+#include "cheb.cuh"
+#include "common.cuh"
+#include "prep.cuh"
+
+namespace egnn {
+
+static thread_local char g_err[512] = {0};
+char* last_error_buf() { return g_err; }
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int pow2_ceil_log2(int64_t x) {
+    int l = 0;
+    while ((int64_t(1) << l) < x) ++l;
+    return l;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int fill_delta(DeltaList& d, const int32_t* r, const int32_t* c, const float* v, int32_t n) {
+    EGNN_REQUIRE(n >= 0 && n <= EGNN_MAX_DELTA, "n_delta out of range");
+    EGNN_REQUIRE(n == 0 || (r && c && v), "delta arrays missing");
+    d.n = n;
+    for (int i = 0; i < n; ++i) { d.row[i] = r[i]; d.col[i] = c[i]; d.val[i] = v[i]; }
+    return EGNN_OK;
+}
+
+// Lane layout and instantiation for one order launch.
+struct OrderConfig {
+    int vec, u, fl_log2, nz_log2, tile, grid_y;
+    bool prescaled;
+};
+
+static OrderConfig choose_config(int64_t n_rows, int64_t nnz, int32_t F) {
+    OrderConfig c{};
+    if (F % 4 == 0) { c.vec = 4; c.u = 1; }
+    else if (F <= 32) { c.vec = 1; c.u = 1; }
+    else { c.vec = 1; c.u = 4; }
+    const int per_lane = c.vec * c.u;
+    int fl = pow2_ceil_log2((F + per_lane - 1) / per_lane);
+    if (c.vec == 1 && c.u == 4) fl = 5;           // u-strided layout wants the full warp
+    if (fl > 5) fl = 5;
+    c.fl_log2 = fl;
+    c.tile = (1 << fl) * per_lane;
+    c.grid_y = (F + c.tile - 1) / c.tile;
+    // non-zeros in parallel: about half the mean row length, within the warp
+    const double mean = n_rows > 0 ? double(nnz) / double(n_rows) : 1.0;
+    int nz = 0;
+    while (nz < 5 - fl && double(1 << (nz + 1)) <= mean * 0.75) ++nz;
+    c.nz_log2 = nz;
+    c.prescaled = (F <= 4);
+    return c;
+}
+
+template <int VEC, int U>
+static void launch_order_vu(const OrderParams& p, bool has_vals, bool prescaled, dim3 grid,
+                            cudaStream_t st) {
+    if (has_vals) {
+        if (prescaled) cheb_order_kernel<VEC, U, true, true><<<grid, kOrderBlock, 0, st>>>(p);
+        else cheb_order_kernel<VEC, U, true, false><<<grid, kOrderBlock, 0, st>>>(p);
+    } else {
+        if (prescaled) cheb_order_kernel<VEC, U, false, true><<<grid, kOrderBlock, 0, st>>>(p);
+        else cheb_order_kernel<VEC, U, false, false><<<grid, kOrderBlock, 0, st>>>(p);
+    }
+}
+
+static int launch_order(const OrderParams& p, const OrderConfig& c, cudaStream_t st) {
+    if (p.n_rows == 0) return EGNN_OK;
+    const int rows_per_block = (kOrderBlock / 32) * (32 >> (c.fl_log2 + c.nz_log2));
+    dim3 grid((unsigned)ceil_div64(p.n_rows, rows_per_block), (unsigned)c.grid_y, 1);
+    const bool has_vals = p.vals != nullptr;
+    if (c.vec == 4) launch_order_vu<4, 1>(p, has_vals, c.prescaled, grid, st);
+    else if (c.u == 1) launch_order_vu<1, 1>(p, has_vals, c.prescaled, grid, st);
+    else launch_order_vu<1, 4>(p, has_vals, c.prescaled, grid, st);
+    EGNN_LAUNCH_CHECK("cheb_order_kernel launch");
+    return EGNN_OK;
+}
+
+static int grid_for(int64_t work_items, int threads) {
+    int64_t b = ceil_div64(work_items, threads);
+    const int64_t cap = (int64_t)kSmCountB200 * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace egnn
+
+using namespace egnn;
+
+extern "C" {
+
+int egnn_abi_version(void) { return 1; }
+
+const char* egnn_last_error(void) { return last_error_buf(); }
+
+int egnn_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+    int dev = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    rc = check_cuda(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
+    if (rc) return rc;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (prop.major != 10) {
+        set_error("libegnn_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+        return EGNN_ERR_UNSUPPORTED_ARCH;
+    }
+    return EGNN_OK;
+}
+
+int egnn_dense_to_csr_count(const float* adj, int64_t n, int64_t ld, int32_t* rowptr,
+                            int32_t* nonbinary, egnn_stream_t stream) {
+    EGNN_REQUIRE(adj && rowptr && nonbinary, "null pointer");
+    EGNN_REQUIRE(n >= 0 && ld >= n, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_cuda(cudaMemsetAsync(nonbinary, 0, sizeof(int32_t), st), "memset nonbinary");
+    if (rc) return rc;
+    if (n > 0) {
+        dense_count_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(adj, n, ld, rowptr + 1, nonbinary);
+        EGNN_LAUNCH_CHECK("dense_count_kernel launch");
+    }
+    rowptr_scan_kernel<<<1, 1024, 0, st>>>(rowptr, n);
+    EGNN_LAUNCH_CHECK("rowptr_scan_kernel launch");
+    return EGNN_OK;
+}
+
+int egnn_dense_to_csr_fill(const float* adj, int64_t n, int64_t ld, const int32_t* rowptr,
+                           int32_t* colidx, float* vals_or_null, egnn_stream_t stream) {
+    EGNN_REQUIRE(adj && rowptr, "null pointer");
+    EGNN_REQUIRE(n >= 0 && ld >= n, "bad shape");
+    if (n == 0) return EGNN_OK;
+    EGNN_REQUIRE(colidx != nullptr, "null colidx");
+    dense_fill_kernel<<<grid_for(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(adj, n, ld, rowptr, colidx,
+                                                                               vals_or_null);
+    EGNN_LAUNCH_CHECK("dense_fill_kernel launch");
+    return EGNN_OK;
+}
+
+int egnn_graph_prep(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null, int64_t n,
+                    float* dinv, uint8_t* iso, float* x0_logdeg, float* w_out_or_null,
+                    float* rowsum_out, float* diag_ws, double* colsum_ws, egnn_stream_t stream) {
+    EGNN_REQUIRE(rowptr && dinv && iso && rowsum_out && diag_ws && colsum_ws, "null pointer");
+    EGNN_REQUIRE(n >= 0, "bad shape");
+    if (n == 0) return EGNN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_cuda(cudaMemsetAsync(colsum_ws, 0, sizeof(double) * n, st), "memset colsum");
+    if (rc) return rc;
+    const int g = grid_for(n * 32, 256);
+    if (vals_or_null)
+        degree_kernel<true><<<g, 256, 0, st>>>(rowptr, colidx, vals_or_null, n, rowsum_out, diag_ws, colsum_ws);
+    else
+        degree_kernel<false><<<g, 256, 0, st>>>(rowptr, colidx, nullptr, n, rowsum_out, diag_ws, colsum_ws);
+    EGNN_LAUNCH_CHECK("degree_kernel launch");
+    normaliser_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(colsum_ws, diag_ws, rowsum_out, n, dinv, iso,
+                                                                   x0_logdeg, w_out_or_null);
+    EGNN_LAUNCH_CHECK("normaliser_kernel launch");
+    return EGNN_OK;
+}
+
+int egnn_patch_degrees(const float* w_base, const float* rowsum_base, const float* dinv_base,
+                       const uint8_t* iso_base, const float* x0_base, int64_t n,
+                       const int32_t* delta_row_host, const int32_t* delta_col_host,
+                       const float* delta_val_host, int32_t n_delta, float* dinv_out, uint8_t* iso_out,
+                       float* x0_out, egnn_stream_t stream) {
+    EGNN_REQUIRE(w_base && rowsum_base && dinv_base && iso_base && x0_base && dinv_out && iso_out && x0_out,
+                 "null pointer");
+    DeltaList d;
+    int rc = fill_delta(d, delta_row_host, delta_col_host, delta_val_host, n_delta);
+    if (rc) return rc;
+    for (int i = 0; i < n_delta; ++i)
+        EGNN_REQUIRE(d.row[i] >= 0 && d.row[i] < n && d.col[i] >= 0 && d.col[i] < n, "delta index out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = check_cuda(cudaMemcpyAsync(dinv_out, dinv_base, sizeof(float) * n, cudaMemcpyDeviceToDevice, st), "copy dinv");
+    if (rc) return rc;
+    rc = check_cuda(cudaMemcpyAsync(iso_out, iso_base, sizeof(uint8_t) * n, cudaMemcpyDeviceToDevice, st), "copy iso");
+    if (rc) return rc;
+    rc = check_cuda(cudaMemcpyAsync(x0_out, x0_base, sizeof(float) * n, cudaMemcpyDeviceToDevice, st), "copy x0");
+    if (rc) return rc;
+    if (n_delta > 0) {
+        patch_degrees_kernel<<<1, EGNN_MAX_DELTA, 0, st>>>(w_base, rowsum_base, d, dinv_out, iso_out, x0_out);
+        EGNN_LAUNCH_CHECK("patch_degrees_kernel launch");
+    }
+    return EGNN_OK;
+}
+
+size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f) {
+    // two T ping-pong slabs + two pre-scaled gather slabs (narrow F only)
+    const size_t slab = align_up(sizeof(float) * (size_t)n * (size_t)f, 256);
+    return slab * (f <= 4 ? 4 : 2) + 256;
+}
+
+int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null,
+                      const float* dinv, const uint8_t* iso, const float* x0, int64_t n, int64_t nnz,
+                      int32_t f, int32_t k, int32_t n_scales, const float* coeffs_host, float op_scale, float op_shift,
+                      float* out, float* t_all_or_null, int32_t normalize_l1,
+                      const int32_t* delta_row_host, const int32_t* delta_col_host,
+                      const float* delta_val_host, int32_t n_delta, void* workspace,
+                      size_t workspace_bytes, egnn_stream_t stream, void* const* order_events_host) {
+    EGNN_REQUIRE(rowptr && dinv && iso && x0 && out && coeffs_host, "null pointer");
+    EGNN_REQUIRE(nnz == 0 || colidx, "null colidx");
+    EGNN_REQUIRE(n >= 0 && n < (int64_t(1) << 31) && nnz >= 0 && nnz < (int64_t(1) << 31), "n/nnz out of int32 range");
+    EGNN_REQUIRE(f >= 1, "f must be >= 1");
+    EGNN_REQUIRE(k >= 0 && k <= EGNN_MAX_ORDER, "k out of range");
+    EGNN_REQUIRE(n_scales >= 1 && n_scales <= EGNN_MAX_SCALES, "n_scales out of range");
+    if (n == 0) return EGNN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    OrderParams p{};
+    int rc = fill_delta(p.delta, delta_row_host, delta_col_host, delta_val_host, n_delta);
+    if (rc) return rc;
+    for (int i = 0; i < n_delta; ++i)
+        EGNN_REQUIRE(p.delta.row[i] >= 0 && p.delta.row[i] < n && p.delta.col[i] >= 0 && p.delta.col[i] < n,
+                     "delta index out of range");
+
+    const size_t slab_elems = (size_t)n * (size_t)f;
+    if (k == 0) {
+        for (int s = 0; s < n_scales; ++s) p.c_prev[s] = coeffs_host[s];
+        order0_kernel<<<grid_for((int64_t)slab_elems * n_scales, 256), 256, 0, st>>>(x0, out, n, f, n_scales, p);
+        EGNN_LAUNCH_CHECK("order0_kernel launch");
+        if (t_all_or_null) {
+            rc = check_cuda(cudaMemcpyAsync(t_all_or_null, x0, sizeof(float) * slab_elems, cudaMemcpyDeviceToDevice, st), "copy T0");
+            if (rc) return rc;
+        }
+        if (normalize_l1) {
+            l1_normalize_kernel<<<grid_for(n * n_scales * 32, 256), 256, 0, st>>>(out, n * n_scales, f);
+            EGNN_LAUNCH_CHECK("l1_normalize_kernel launch");
+        }
+        return EGNN_OK;
+    }
+
+    const OrderConfig cfg = choose_config(n, nnz, f);
+    const size_t need = egnn_cheb_workspace_bytes(n, f);
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return EGNN_ERR_WORKSPACE;
+    }
+    const size_t slab = align_up(sizeof(float) * slab_elems, 256);
+    char* ws = (char*)align_up((size_t)workspace, 256);
+    float* tbuf[2] = {(float*)ws, (float*)(ws + slab)};
+    float* ybuf[2] = {(float*)(ws + 2 * slab), (float*)(ws + 3 * slab)};
+
+    if (t_all_or_null) {
+        rc = check_cuda(cudaMemcpyAsync(t_all_or_null, x0, sizeof(float) * slab_elems, cudaMemcpyDeviceToDevice, st), "copy T0");
+        if (rc) return rc;
+    }
+    if (cfg.prescaled) {
+        prescale_kernel<<<grid_for((int64_t)slab_elems, 256), 256, 0, st>>>(x0, dinv, ybuf[0], n, f, 0);
+        EGNN_LAUNCH_CHECK("prescale_kernel launch");
+    }
+
+    p.rowptr = rowptr; p.colidx = colidx; p.vals = vals_or_null; p.dinv = dinv; p.iso = iso;
+    p.out = out; p.acc_ws = nullptr; p.n_rows = n; p.row0 = 0; p.F = f; p.S = n_scales;
+    p.a = op_scale; p.b = op_shift; p.mode = 0; p.fl_log2 = cfg.fl_log2; p.nz_log2 = cfg.nz_log2;
+
+    const bool fuse_norm = normalize_l1 && cfg.grid_y == 1;
+    const float* t_prev = x0;         // T_{k-1}
+    const float* t_prev2 = nullptr;   // T_{k-2}
+    for (int order = 1; order <= k; ++order) {
+        const bool last = order == k;
+        float* t_out;
+        if (t_all_or_null) t_out = t_all_or_null + (size_t)order * slab_elems;
+        else if (last) t_out = nullptr;                       // T_K itself is never read again
+        else if (order == 1) t_out = tbuf[0];
+        else if (order == 2) t_out = tbuf[1];
+        else t_out = const_cast<float*>(t_prev2);             // overwrite T_{k-2} in place
+        p.first = order == 1;
+        p.normalize = last && fuse_norm;
+        p.tprev_own = t_prev;
+        p.tprev2_own = t_prev2;
+        p.tk_own = t_out;
+        p.gsrc = cfg.prescaled ? ybuf[(order - 1) & 1] : t_prev;
+        p.y_own = (cfg.prescaled && !last) ? ybuf[order & 1] : nullptr;
+        for (int s = 0; s < n_scales; ++s) {
+            p.c_prev[s] = coeffs_host[s * (k + 1) + order - 1];
+            p.c_k[s] = coeffs_host[s * (k + 1) + order];
+        }
+        if (order_events_host) {
+            rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1)], st), "event record");
+            if (rc) return rc;
+        }
+        rc = launch_order(p, cfg, st);
+        if (rc) return rc;
+        if (order_events_host) {
+            rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1) + 1], st), "event record");
+            if (rc) return rc;
+        }
+        t_prev2 = t_prev;
+        t_prev = t_out;
+    }
+    if (normalize_l1 && !fuse_norm) {
+        l1_normalize_kernel<<<grid_for(n * n_scales * 32, 256), 256, 0, st>>>(out, n * n_scales, f);
+        EGNN_LAUNCH_CHECK("l1_normalize_kernel launch");
+    }
+    return EGNN_OK;
+}
+
+int egnn_cheb_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_local,
+                            const int32_t* rowptr_remote, const int32_t* colidx_remote,
+                            const float* dinv_full, const uint8_t* iso_full, const float* t_prev_full,
+                            const float* t_prev_local, const float* t_prev2_local, float* t_out_local,
+                            float* out_local, float* acc_ws, int64_t n, int64_t nnz_hint,
+                            int64_t row_begin, int64_t row_end, int32_t f, int32_t order, int32_t k_max,
+                            int32_t n_scales, const float* coeffs_host, float op_scale, float op_shift,
+                            int32_t normalize_l1, int32_t phase, egnn_stream_t stream) {
+    EGNN_REQUIRE(dinv_full && iso_full && out_local && coeffs_host && t_prev_local, "null pointer");
+    EGNN_REQUIRE(row_begin >= 0 && row_end >= row_begin && row_end <= n, "bad row range");
+    EGNN_REQUIRE(order >= 1 && order <= k_max && k_max <= EGNN_MAX_ORDER, "bad order");
+    EGNN_REQUIRE(n_scales >= 1 && n_scales <= EGNN_MAX_SCALES, "n_scales out of range");
+    EGNN_REQUIRE(phase >= 0 && phase <= 2, "bad phase");
+    EGNN_REQUIRE(order == 1 || t_prev2_local, "T_{k-2} missing");
+    const int64_t rows = row_end - row_begin;
+    if (rows == 0) return EGNN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    OrderParams p{};
+    p.delta.n = 0;
+    p.vals = nullptr; p.dinv = dinv_full; p.iso = iso_full;
+    p.tprev_own = t_prev_local; p.tprev2_own = t_prev2_local; p.tk_own = t_out_local; p.y_own = nullptr;
+    p.out = out_local; p.acc_ws = acc_ws; p.n_rows = rows; p.row0 = row_begin; p.F = f; p.S = n_scales;
+    p.a = op_scale; p.b = op_shift; p.first = order == 1;
+    for (int s = 0; s < n_scales; ++s) {
+        p.c_prev[s] = coeffs_host[s * (k_max + 1) + order - 1];
+        p.c_k[s] = coeffs_host[s * (k_max + 1) + order];
+    }
+    OrderConfig cfg = choose_config(rows, nnz_hint, f);
+    cfg.prescaled = false;            // sharded slabs carry plain T_k (what the exchange moves)
+    p.fl_log2 = cfg.fl_log2; p.nz_log2 = cfg.nz_log2;
+    const bool last = order == k_max;
+    const bool fuse_norm = normalize_l1 && cfg.grid_y == 1;
+    int rc;
+    if (phase == 0) {                 // local columns: gathers hit the rank's own slab
+        EGNN_REQUIRE(rowptr_local && acc_ws, "local half missing");
+        p.rowptr = rowptr_local; p.colidx = colidx_local;
+        p.gsrc = t_prev_local - row_begin * (int64_t)f;      // indexed by global column, only own rows touched
+        p.mode = 1; p.normalize = 0;
+        return launch_order(p, cfg, st);
+    }
+    EGNN_REQUIRE(t_prev_full != nullptr, "gathered T_{k-1} missing");
+    p.gsrc = t_prev_full;
+    p.normalize = last && fuse_norm;
+    if (phase == 1) {                 // remote columns + epilogue
+        EGNN_REQUIRE(rowptr_remote && acc_ws, "remote half missing");
+        p.rowptr = rowptr_remote; p.colidx = colidx_remote; p.mode = 2;
+    } else {                          // one launch over the unsplit rows
+        EGNN_REQUIRE(rowptr_local != nullptr, "csr missing");
+        p.rowptr = rowptr_local; p.colidx = colidx_local; p.mode = 0;
+    }
+    rc = launch_order(p, cfg, st);
+    if (rc) return rc;
+    if (last && normalize_l1 && !fuse_norm) {
+        l1_normalize_kernel<<<grid_for(rows * n_scales * 32, 256), 256, 0, st>>>(out_local, rows * n_scales, f);
+        EGNN_LAUNCH_CHECK("l1_normalize_kernel launch");
+    }
+    return EGNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+"""Device-resident graph for the wavelet path: CSR adjacency + the degree
+vectors that stand in for the (never materialised) normalised Laplacian.
+
+Replaces the reference's host-side detour ``csr_matrix(adj.cpu().numpy())``
+(calibration/WATS.py:99) and ``csgraph.laplacian`` (calibration/WATS.py:26).
+All arithmetic happens in libegnn_b200 kernels; torch is used for allocation,
+streams and (for inputs that are not already a dense device tensor) format
+plumbing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+__all__ = ["CsrGraph", "as_graph"]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class CsrGraph:
+    """CSR adjacency in HBM plus ``dinv``/``iso``/``x0`` (scipy Laplacian
+    semantics, see include/egnn_b200.h::egnn_graph_prep).
+
+    ``vals is None`` means a binary adjacency (every reference call site).
+    """
+
+    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, vals: Optional[torch.Tensor], n: int):
+        _cabi.require_device()
+        if rowptr.dtype != torch.int32 or colidx.dtype != torch.int32:
+            raise TypeError("rowptr/colidx must be int32")
+        if not (rowptr.is_cuda and colidx.is_cuda):
+            raise _cabi.EgnnError("CsrGraph arrays must live on the CUDA device")
+        if rowptr.numel() != n + 1:
+            raise ValueError("rowptr must have n+1 entries")
+        self.n = int(n)
+        self.rowptr = rowptr.contiguous()
+        self.colidx = colidx.contiguous()
+        self.vals = None if vals is None else vals.to(torch.float32).contiguous()
+        self.nnz = int(colidx.numel())
+        if self.nnz >= 2 ** 31:
+            raise ValueError("nnz must fit int32")
+        self.device = rowptr.device
+        self._prepare()
+
+    # -- construction -------------------------------------------------------
+    @classmethod
+    def from_dense(cls, adj: torch.Tensor) -> "CsrGraph":
+        """Dense ``[N,N]`` float32 device tensor -> CSR, entirely on the GPU
+        (two streaming passes over the matrix; replaces WATS.py:99)."""
+        _cabi.require_device()
+        if adj.dim() != 2 or adj.shape[0] != adj.shape[1]:
+            raise ValueError("adjacency must be square")
+        adj = adj.detach()
+        if not adj.is_cuda:
+            adj = adj.to("cuda", non_blocking=True)
+        if adj.dtype != torch.float32:
+            adj = adj.to(torch.float32)
+        if adj.stride(1) != 1:
+            adj = adj.contiguous()
+        n = adj.shape[0]
+        lib = _cabi.load()
+        with torch.cuda.device(adj.device):
+            rowptr = torch.empty(n + 1, dtype=torch.int32, device=adj.device)
+            flag = torch.empty(1, dtype=torch.int32, device=adj.device)
+            _cabi.check(lib.egnn_dense_to_csr_count(_cabi.ptr(adj), n, adj.stride(0), _cabi.ptr(rowptr),
+                                                    _cabi.ptr(flag), _stream()), "egnn_dense_to_csr_count")
+            meta = torch.stack([rowptr[n], flag[0]]).cpu()       # one sync: nnz + binary flag
+            nnz, nonbinary = int(meta[0]), bool(meta[1])
+            colidx = torch.empty(nnz, dtype=torch.int32, device=adj.device)
+            vals = torch.empty(nnz, dtype=torch.float32, device=adj.device) if nonbinary else None
+            _cabi.check(lib.egnn_dense_to_csr_fill(_cabi.ptr(adj), n, adj.stride(0), _cabi.ptr(rowptr),
+                                                   _cabi.ptr(colidx), _cabi.ptr(vals), _stream()),
+                        "egnn_dense_to_csr_fill")
+        return cls(rowptr, colidx, vals, n)
+
+    @classmethod
+    def from_host_csr(cls, rowptr, colidx, vals, n: int, device="cuda") -> "CsrGraph":
+        """Host CSR buffers (int32 torch tensors, ideally pinned) -> device
+        graph: asynchronous H2D copies on the current stream, then the degree
+        pass.  This is the entry the host-buffer (end-to-end) timing uses."""
+        _cabi.require_device()
+        rp = torch.as_tensor(rowptr).to(device, non_blocking=True)
+        ci = torch.as_tensor(colidx).to(device, non_blocking=True)
+        vv = None if vals is None else torch.as_tensor(vals).to(device, non_blocking=True)
+        return cls(rp, ci, vv, n)
+
+    @classmethod
+    def from_scipy(cls, mat, device="cuda") -> "CsrGraph":
+        import scipy.sparse as sp
+        m = sp.csr_matrix(mat)
+        m.sum_duplicates()
+        m.eliminate_zeros()
+        m.sort_indices()
+        data = np.asarray(m.data, dtype=np.float32)
+        vals = None if np.all(data == 1.0) else torch.from_numpy(data).to(device)
+        return cls(torch.from_numpy(m.indptr.astype(np.int32)).to(device),
+                   torch.from_numpy(m.indices.astype(np.int32)).to(device), vals, m.shape[0])
+
+    @classmethod
+    def from_edge_index(cls, edge_index, n: int, edge_weight=None, device="cuda") -> "CsrGraph":
+        """``(edge_index [2,E], N)``; duplicate edges are summed like scipy does."""
+        ei = torch.as_tensor(edge_index).to(device=device, dtype=torch.int64)
+        key = ei[0] * n + ei[1]
+        if edge_weight is None:
+            uniq, counts = torch.unique(key, return_counts=True)
+            vals = None if bool((counts == 1).all()) else counts.to(torch.float32)
+        else:
+            w = torch.as_tensor(edge_weight).to(device=device, dtype=torch.float32)
+            uniq, inv = torch.unique(key, return_inverse=True)
+            vals = torch.zeros(uniq.numel(), dtype=torch.float32, device=device).index_add_(0, inv, w)
+            keep = vals != 0
+            uniq, vals = uniq[keep], vals[keep]
+            if bool((vals == 1).all()):
+                vals = None
+        rows = uniq // n
+        rowptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+        rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+        return cls(rowptr.to(torch.int32), (uniq % n).to(torch.int32), vals, n)
+
+    # -- degree vectors -----------------------------------------------------
+    def _prepare(self):
+        n, dev = self.n, self.device
+        lib = _cabi.load()
+        with torch.cuda.device(dev):
+            self.dinv = torch.empty(n, dtype=torch.float32, device=dev)
+            self.iso = torch.empty(n, dtype=torch.uint8, device=dev)
+            self.x0 = torch.empty(n, dtype=torch.float32, device=dev)
+            self.w = torch.empty(n, dtype=torch.float32, device=dev)
+            self.rowsum = torch.empty(n, dtype=torch.float32, device=dev)
+            diag = torch.empty(n, dtype=torch.float32, device=dev)
+            colsum = torch.empty(n, dtype=torch.float64, device=dev)
+            _cabi.check(lib.egnn_graph_prep(_cabi.ptr(self.rowptr), _cabi.ptr(self.colidx), _cabi.ptr(self.vals), n,
+                                            _cabi.ptr(self.dinv), _cabi.ptr(self.iso), _cabi.ptr(self.x0),
+                                            _cabi.ptr(self.w), _cabi.ptr(self.rowsum), _cabi.ptr(diag),
+                                            _cabi.ptr(colsum), _stream()), "egnn_graph_prep")
+
+    def patched(self, delta_rows: Sequence[int], delta_cols: Sequence[int], delta_vals: Sequence[float]):
+        """(dinv, iso, x0) of this graph with edge flips applied (UGCA
+        recompute): flip e adds ``delta_vals[e]`` to ``A[rows[e], cols[e]]``."""
+        n, dev = self.n, self.device
+        nd = len(delta_rows)
+        lib = _cabi.load()
+        with torch.cuda.device(dev):
+            dinv = torch.empty_like(self.dinv)
+            iso = torch.empty_like(self.iso)
+            x0 = torch.empty_like(self.x0)
+            _cabi.check(lib.egnn_patch_degrees(
+                _cabi.ptr(self.w), _cabi.ptr(self.rowsum), _cabi.ptr(self.dinv), _cabi.ptr(self.iso),
+                _cabi.ptr(self.x0), n,
+                _cabi.host_array(C.c_int32, [int(v) for v in delta_rows]),
+                _cabi.host_array(C.c_int32, [int(v) for v in delta_cols]),
+                _cabi.host_array(C.c_float, [float(v) for v in delta_vals]), nd,
+                _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(x0), _stream()), "egnn_patch_degrees")
+        return dinv, iso, x0
+
+    def to_scipy(self):
+        """Host copy as scipy CSR float32 (tests / oracle side only)."""
+        import scipy.sparse as sp
+        data = np.ones(self.nnz, np.float32) if self.vals is None else self.vals.cpu().numpy()
+        return sp.csr_matrix((data, self.colidx.cpu().numpy(), self.rowptr.cpu().numpy()),
+                             shape=(self.n, self.n))
+
+
+def as_graph(adj, device="cuda") -> CsrGraph:
+    """Accept what callers of the reference hold: dense torch / numpy, scipy
+    sparse, torch sparse, ``(edge_index, N)`` or an existing :class:`CsrGraph`."""
+    if isinstance(adj, CsrGraph):
+        return adj
+    _cabi.require_device()
+    if hasattr(adj, "graph") and isinstance(getattr(adj, "graph"), CsrGraph):
+        return adj.graph
+    if isinstance(adj, tuple) and len(adj) == 2:
+        return CsrGraph.from_edge_index(adj[0], int(adj[1]), device=device)
+    if isinstance(adj, torch.Tensor):
+        if adj.layout in (torch.sparse_coo, torch.sparse_csr):
+            coo = adj.to_sparse_coo().coalesce()
+            return CsrGraph.from_edge_index(coo.indices(), adj.shape[0], coo.values(), device=device)
+        return CsrGraph.from_dense(adj if adj.is_cuda else adj.to(device))
+    try:
+        import scipy.sparse as sp
+        if sp.issparse(adj):
+            return CsrGraph.from_scipy(adj, device=device)
+    except ImportError:       # pragma: no cover
+        pass
+    arr = np.asarray(adj)
+    if arr.ndim == 2:
+        return CsrGraph.from_dense(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(device))
+    raise TypeError(f"cannot interpret {type(adj)!r} as an adjacency")

@@ -1,0 +1,321 @@
+"""Drop-in host side of the WATS wavelet-feature path (calibration/WATS.py).
+
+Same names, positional signatures and defaults as the reference:
+
+* ``compute_normalized_laplacian(adj)``            (calibration/WATS.py:24-27)
+* ``chebyshev_polynomials(L, k, X0)``              (calibration/WATS.py:29-37)
+* ``graph_wavelet_features(adj_matrix, k=3, s=0.8)`` (calibration/WATS.py:39-74)
+* ``WATS(base_model, features, labels, adj, val_mask)`` (calibration/WATS.py:76-170)
+
+New behaviour is keyword-only.  All arithmetic of the path runs in
+libegnn_b200 (hand-written sm_100a CUDA behind a C ABI); this module is tensor
+plumbing.  There is no CPU fallback: without the shared library or a CUDA
+device every entry point raises ``EgnnError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _cabi
+from .graph import CsrGraph, as_graph
+
+__all__ = ["LaplacianOperator", "compute_normalized_laplacian", "chebyshev_polynomials",
+           "graph_wavelet_features", "heat_coefficients", "WaveletResult", "WATS", "accuracy"]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def heat_coefficients(k: int, s) -> np.ndarray:
+    """``alpha[j, i] = exp(-s_j * i)`` (calibration/WATS.py:65), float64 on the
+    host, rounded to float32 when handed to the kernel."""
+    s = np.atleast_1d(np.asarray(s, dtype=np.float64))
+    return np.exp(-s[:, None] * np.arange(k + 1, dtype=np.float64)[None, :])
+
+
+class WaveletResult:
+    """Outputs of one fused pass: ``features`` ``[N, S*F]`` (what the reference
+    returns), plus the pre-normalisation pieces parity checks need."""
+
+    def __init__(self, features, orders=None, combined=None):
+        self.features = features
+        self.orders = orders          # list of K+1 [N,F] tensors or None
+        self.combined = combined      # [N, S, F] un-normalised S or None
+
+
+def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_scale: float,
+              op_shift: float, normalize: bool, want_orders: bool, deltas=None,
+              degree_vectors=None, order_events=None):
+    """One call of egnn_cheb_wavelet.  Returns (out [N,S,F], t_all or None)."""
+    lib = _cabi.load()
+    n, dev = graph.n, graph.device
+    if x0.dim() == 1:
+        x0 = x0.unsqueeze(1)
+    if x0.shape[0] != n:
+        raise ValueError(f"X0 has {x0.shape[0]} rows, graph has {n} nodes")
+    x0 = x0.detach().to(device=dev, dtype=torch.float32).contiguous()
+    f = int(x0.shape[1])
+    n_scales = int(coeffs.shape[0])
+    if coeffs.shape[1] != k + 1:
+        raise ValueError("coeffs must be [S, K+1]")
+    dinv, iso = (graph.dinv, graph.iso) if degree_vectors is None else degree_vectors
+    d_rows, d_cols, d_vals = ([], [], []) if deltas is None else deltas
+    with torch.cuda.device(dev):
+        out = torch.empty((n, n_scales, f), dtype=torch.float32, device=dev)
+        t_all = torch.empty((k + 1, n, f), dtype=torch.float32, device=dev) if want_orders else None
+        ws_bytes = int(lib.egnn_cheb_workspace_bytes(n, f))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        coeffs32 = np.ascontiguousarray(coeffs, dtype=np.float32)
+        _cabi.check(lib.egnn_cheb_wavelet(
+            _cabi.ptr(graph.rowptr), _cabi.ptr(graph.colidx), _cabi.ptr(graph.vals), _cabi.ptr(dinv),
+            _cabi.ptr(iso), _cabi.ptr(x0), n, graph.nnz, f, k, n_scales,
+            coeffs32.ctypes.data_as(C.c_void_p), float(op_scale), float(op_shift),
+            _cabi.ptr(out), _cabi.ptr(t_all), 1 if normalize else 0,
+            _cabi.host_array(C.c_int32, [int(v) for v in d_rows]),
+            _cabi.host_array(C.c_int32, [int(v) for v in d_cols]),
+            _cabi.host_array(C.c_float, [float(v) for v in d_vals]), len(d_rows),
+            _cabi.ptr(ws), ws_bytes, _stream(), order_events), "egnn_cheb_wavelet")
+    return out, t_all
+
+
+class LaplacianOperator:
+    """``scale * L_sym + shift * I`` of a device graph, never materialised.
+
+    What ``compute_normalized_laplacian`` returns (scale 1, shift 0).  It
+    supports exactly the algebra the reference applies to scipy's Laplacian -
+    ``(2 / lambda_max) * L - identity(N)`` (calibration/WATS.py:55), ``2 * L``
+    and ``L @ X`` (calibration/WATS.py:34,36) - so the reference's own function
+    bodies run unchanged on it.
+    """
+
+    def __init__(self, graph: CsrGraph, scale: float = 1.0, shift: float = 0.0):
+        self.graph = graph
+        self.scale = float(scale)
+        self.shift = float(shift)
+        self.shape = (graph.n, graph.n)
+
+    def __rmul__(self, c):
+        return LaplacianOperator(self.graph, self.scale * float(c), self.shift * float(c))
+
+    __mul__ = __rmul__
+
+    @staticmethod
+    def _identity_multiple(other, n):
+        """c such that other == c * I_n, for scipy / numpy / torch identities."""
+        try:
+            import scipy.sparse as sp
+            if sp.issparse(other):
+                if other.shape != (n, n):
+                    raise ValueError("shape mismatch")
+                d = other.diagonal()
+                if other.nnz > n or (other - sp.diags(d)).nnz != 0 or not np.all(d == d[0]):
+                    raise ValueError("only multiples of the identity can be added to the operator")
+                return float(d[0])
+        except ImportError:   # pragma: no cover
+            pass
+        raise TypeError("only multiples of a scipy identity can be added to the operator")
+
+    def __sub__(self, other):
+        return LaplacianOperator(self.graph, self.scale, self.shift - self._identity_multiple(other, self.graph.n))
+
+    def __add__(self, other):
+        return LaplacianOperator(self.graph, self.scale, self.shift + self._identity_multiple(other, self.graph.n))
+
+    def __matmul__(self, x):
+        """One operator application through the fused kernel (order-1 pass)."""
+        xt = torch.as_tensor(x)
+        vec = xt.dim() == 1
+        out, _ = _run_cheb(self.graph, xt, 1, np.array([[0.0, 1.0]]), self.scale, self.shift, False, False)
+        y = out[:, 0, :]
+        return y[:, 0] if vec else y
+
+    def rescaled(self, lambda_max: float = 2.0) -> "LaplacianOperator":
+        """``(2/lambda_max) * L - I`` (calibration/WATS.py:55)."""
+        c = 2.0 / float(lambda_max)
+        return LaplacianOperator(self.graph, self.scale * c, self.shift * c - 1.0)
+
+
+def compute_normalized_laplacian(adj) -> LaplacianOperator:
+    """``L_sym = I - D^-1/2 A D^-1/2`` with scipy's ``csgraph.laplacian(adj,
+    normed=True)`` semantics (calibration/WATS.py:24-27), as an implicit
+    device operator: CSR adjacency + degree vectors, no materialised L."""
+    return LaplacianOperator(as_graph(adj))
+
+
+def chebyshev_polynomials(L, k, X0):
+    """``[T_0 .. T_k]`` with ``T_1 = L X0``, ``T_i = 2 L T_{i-1} - T_{i-2}``
+    (calibration/WATS.py:29-37).  ``L`` is a :class:`LaplacianOperator`
+    (normally the rescaled one); returns k+1 float32 device tensors ``[N,F]``."""
+    if not isinstance(L, LaplacianOperator):
+        raise TypeError("L must come from compute_normalized_laplacian (LaplacianOperator)")
+    k = int(k)
+    coeffs = np.zeros((1, k + 1))
+    _, t_all = _run_cheb(L.graph, torch.as_tensor(X0), k, coeffs, L.scale, L.shift, False, True)
+    return [t_all[i] for i in range(k + 1)]
+
+
+def graph_wavelet_features(adj_matrix, k=3, s=0.8, *, X0=None, lambda_max: float = 2.0,
+                           normalize: bool = True, return_parts: bool = False, deltas=None,
+                           _order_events=None):
+    """Graph wavelet features by Chebyshev approximation of the heat kernel
+    (calibration/WATS.py:39-74).
+
+    Positional behaviour is the reference's: ``X0 = log1p(degree)``, ``k = 3``,
+    one scale ``s = 0.8``, ``lambda_max = 2``, row-L1-normalised ``[N, F]``.
+    Keyword-only extensions: ``s`` may be a sequence (all scales accumulated in
+    the same pass, output ``[N, len(s)*F]``); ``X0`` a custom ``[N,F]`` signal;
+    ``lambda_max``; ``return_parts`` -> :class:`WaveletResult` with the orders
+    and the un-normalised combination; ``deltas=(rows, cols, vals)`` applies
+    edge flips on top of the graph without rebuilding it (UGCA recompute).
+    Returns a float32 tensor on the graph's device.
+    """
+    graph = as_graph(adj_matrix)
+    k = int(k)
+    coeffs = heat_coefficients(k, s)
+    degree_vectors = None
+    x0 = graph.x0 if X0 is None else torch.as_tensor(X0)
+    if deltas is not None and len(deltas[0]) > 0:
+        dinv, iso, x0_patched = graph.patched(*deltas)
+        degree_vectors = (dinv, iso)
+        if X0 is None:
+            x0 = x0_patched
+    else:
+        deltas = None
+    op_scale = 2.0 / float(lambda_max)
+    if return_parts:
+        comb, t_all = _run_cheb(graph, x0, k, coeffs, op_scale, -1.0, False, True, deltas, degree_vectors)
+        feats = comb / (comb.abs().sum(dim=2, keepdim=True) + 1e-8) if normalize else comb
+        feats = feats.reshape(graph.n, -1)
+        return WaveletResult(feats, [t_all[i] for i in range(k + 1)], comb)
+    out, _ = _run_cheb(graph, x0, k, coeffs, op_scale, -1.0, normalize, False, deltas, degree_vectors,
+                       _order_events)
+    return out.reshape(graph.n, -1)
+
+
+def accuracy(outputs, labels):
+    """Fraction of argmax hits (calibration/utils.py:139-167)."""
+    if not isinstance(outputs, torch.Tensor) or not isinstance(labels, torch.Tensor):
+        raise ValueError("Input arrays must be of type torch.Tensor.")
+    if outputs.shape[0] != labels.shape[0]:
+        raise ValueError("Input arrays must have the same number of elements.")
+    return (torch.sum(torch.argmax(outputs, dim=1) == labels) / labels.shape[0]).item()
+
+
+class WATS(nn.Module):
+    """Wavelet-Aware Temperature Scaling (calibration/WATS.py:76-170).
+
+    Same constructor, attributes (``wavelet_feats`` stays a plain attribute,
+    not a buffer, so ``state_dict`` keys match the reference), ``forward`` and
+    ``calib_train``.  The only difference on the default path is where
+    ``wavelet_feats`` comes from: dense adjacency -> CSR -> fused Chebyshev
+    kernels on the device instead of the host scipy detour (WATS.py:99-100).
+
+    Keyword-only extensions: ``k``, ``s``, ``lambda_max`` (reference constants
+    3 / 0.8 / 2.0), ``recompute_on_forward`` (recompute the features from the
+    ``adj`` passed to ``forward`` - the reference always reuses the cached
+    ones, WATS.py:123), ``train`` (skip ``calib_train`` when False), ``verbose``.
+    ``_features_override`` exists for parity tests only: it injects a feature
+    matrix computed elsewhere so two instances differ in nothing else.
+    """
+
+    def __init__(self, base_model, features, labels, adj, val_mask, *, k: int = 3, s=0.8,
+                 lambda_max: float = 2.0, recompute_on_forward: bool = False, train: bool = True,
+                 verbose: bool = True, _features_override=None):
+        super().__init__()
+        self.device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+        if _features_override is None:
+            _cabi.require_device()
+        self.base_model = base_model.to(self.device)
+        self.x = features.to(self.device)
+        self.y = labels.to(self.device)
+        self.adj = adj.to(self.device)
+        self.val_idx = val_mask.to(self.device)
+        self.k, self.s, self.lambda_max = int(k), s, float(lambda_max)
+        self.recompute_on_forward = bool(recompute_on_forward)
+        self.verbose = bool(verbose)
+
+        if _features_override is not None:
+            self.graph = None
+            self.wavelet_feats = torch.as_tensor(_features_override, dtype=torch.float32).to(self.device)
+        else:
+            self.graph = as_graph(self.adj)
+            self.wavelet_feats = graph_wavelet_features(self.graph, k=self.k, s=self.s,
+                                                        lambda_max=self.lambda_max)
+        self.net = nn.Sequential(
+            nn.Linear(self.wavelet_feats.shape[1], 16),
+            nn.ReLU(),
+            nn.Linear(16, 1)
+        ).to(self.device)
+        for para in self.net.parameters():
+            para.requires_grad = True
+        if train:
+            self.calib_train()
+
+    def features_for(self, adj=None, *, deltas=None):
+        """Wavelet features of a perturbed graph: either a full adjacency
+        (re-converted on the device) or edge flips on top of the base graph
+        (``deltas=(rows, cols, vals)``; no CSR rebuild)."""
+        if deltas is not None:
+            return graph_wavelet_features(self.graph, k=self.k, s=self.s, lambda_max=self.lambda_max,
+                                          deltas=deltas)
+        if adj is None:
+            return self.wavelet_feats
+        return graph_wavelet_features(adj, k=self.k, s=self.s, lambda_max=self.lambda_max)
+
+    def temperatures(self, wavelet_features):
+        t = self.net(wavelet_features).squeeze()
+        return torch.log(torch.exp(t) + torch.tensor(1.1, device=self.device)).to(self.device)
+
+    def forward(self, x, adj, *, deltas=None):
+        x, adj = x.to(self.device), adj.to(self.device)
+        if deltas is not None:
+            wavelet_features = self.features_for(deltas=deltas)
+        elif self.recompute_on_forward and self.graph is not None:
+            wavelet_features = self.features_for(adj)
+        else:
+            wavelet_features = self.wavelet_feats.to(x.device)
+        temperatures = self.temperatures(wavelet_features)
+        logits = self.base_model(x, adj)
+        calibrated_logits = logits / temperatures.unsqueeze(1)
+        return F.log_softmax(calibrated_logits, dim=1)
+
+    def calib_train(self, patience=10):
+        t = time.time()
+        best_loss = float('inf')
+        patience_counter = patience
+        optimizer = torch.optim.Adam(self.net.parameters(), lr=0.01, weight_decay=5e-4)
+        recompute, self.recompute_on_forward = self.recompute_on_forward, False
+        try:
+            for epoch in range(250):
+                self.train()
+                optimizer.zero_grad()
+                output = self(self.x, self.adj)
+                loss = F.nll_loss(output[self.val_idx], self.y[self.val_idx])
+                loss.backward()
+                optimizer.step()
+                with torch.no_grad():
+                    self.eval()
+                    acc = accuracy(output[self.val_idx], self.y[self.val_idx])
+                    if self.verbose:
+                        print(f'epoch: {epoch}', f'loss_calibration: {loss.item():.4f}',
+                              f'acc_calibration: {acc:.4f}', f'time: {time.time() - t:.4f}s')
+                if loss < best_loss:
+                    best_loss = loss
+                    patience_counter = patience
+                else:
+                    patience_counter -= 1
+                if patience_counter <= 0:
+                    if self.verbose:
+                        print(f'Early stopping at epoch {epoch}, best loss: {best_loss:.4f}')
+                    break
+        finally:
+            self.recompute_on_forward = recompute

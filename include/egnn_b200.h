@@ -1,0 +1,162 @@
+/*
+ * egnn_b200.h - C ABI of libegnn_b200.so: the B200 (sm_100a) implementation of
+ * the Chebyshev graph-wavelet feature path of the WATS calibrator.
+ *
+ * The reference (CaptainCuong/Efficient-GNN) has no FFI; its boundary for this
+ * path is three Python functions and one nn.Module in calibration/WATS.py.
+ * Each entry point below names the reference lines it replaces.  The host side
+ * that mirrors the reference's Python signatures lives in
+ * efficient-gnn_b200/wats.py and binds these symbols with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns all buffers (torch tensors in practice) and passes the
+ *     CUDA stream to launch on; the library keeps no state between calls
+ *     except a thread-local last-error string;
+ *   - every function returns 0 on success or a negative egnn_status; nothing
+ *     throws across the ABI;
+ *   - indices are int32 (nnz < 2^31), features float32, row-major.
+ */
+#ifndef EGNN_B200_H
+#define EGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* egnn_stream_t; /* cudaStream_t */
+
+enum egnn_status {
+    EGNN_OK = 0,
+    EGNN_ERR_INVALID_ARG = -1,
+    EGNN_ERR_CUDA = -2,
+    EGNN_ERR_UNSUPPORTED_ARCH = -3,
+    EGNN_ERR_WORKSPACE = -4
+};
+
+#define EGNN_MAX_SCALES 8
+#define EGNN_MAX_ORDER 64
+#define EGNN_MAX_DELTA 64
+
+/* ABI version of this header (bumped on any signature change). */
+int egnn_abi_version(void);
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char* egnn_last_error(void);
+
+/* SM count / compute capability of the current device; fails with
+ * EGNN_ERR_UNSUPPORTED_ARCH when the device is not sm_100. */
+int egnn_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- dense adjacency -> CSR ------------------------------------------------
+ * Replaces `csr_matrix(adj.cpu().numpy())` (calibration/WATS.py:99): the
+ * device->host copy of the dense [N,N] float32 adjacency and scipy's dense
+ * scan.  Pass 1 counts stored (non-zero) entries per row and writes the
+ * exclusive scan to rowptr[0..n]; *nonbinary (device int32) is set to 1 when
+ * any stored value differs from 1.0f.  The caller reads rowptr[n], allocates
+ * colidx (and vals when non-binary) and runs pass 2.  ld = row stride.      */
+int egnn_dense_to_csr_count(const float* adj, int64_t n, int64_t ld,
+                            int32_t* rowptr, int32_t* nonbinary,
+                            egnn_stream_t stream);
+int egnn_dense_to_csr_fill(const float* adj, int64_t n, int64_t ld,
+                           const int32_t* rowptr, int32_t* colidx,
+                           float* vals_or_null, egnn_stream_t stream);
+
+/* ---- graph preparation -----------------------------------------------------
+ * Replaces scipy `csgraph.laplacian(adj, normed=True)` as called by
+ * compute_normalized_laplacian (calibration/WATS.py:24-27) and the degree
+ * signal of calibration/WATS.py:58-59, without materialising L:
+ *   w_j     = colsum_j(A) - A_jj            (in-degree, self loops excluded)
+ *   iso_j   = (w_j == 0)
+ *   dinv_j  = iso_j ? 1 : 1/sqrt(w_j)
+ *   x0_i    = log1p(rowsum_i(A))            (self loops and weights included)
+ * vals_or_null == NULL means a binary adjacency (all stored values 1).
+ * Outputs dinv/iso/x0_logdeg (x0 may be NULL), w_out_or_null (the float32 w
+ * before the sqrt) and rowsum_out, the base vectors egnn_patch_degrees needs.
+ * diag_ws: [n] float32 scratch; colsum_ws: [n] float64 scratch.              */
+int egnn_graph_prep(const int32_t* rowptr, const int32_t* colidx,
+                    const float* vals_or_null, int64_t n,
+                    float* dinv, uint8_t* iso, float* x0_logdeg,
+                    float* w_out_or_null, float* rowsum_out,
+                    float* diag_ws, double* colsum_ws, egnn_stream_t stream);
+
+/* UGCA recompute (the point where calib_attack/calib_fga.py:868,908,952 call
+ * the calibrated surrogate on a perturbed adjacency): copies dinv/iso/x0 of
+ * the base graph into the *_out vectors and re-derives the entries of every
+ * node an edge flip touches.  Flip e adds delta_val[e] to
+ * A[delta_row[e], delta_col[e]] (host arrays, n_delta <= EGNN_MAX_DELTA).   */
+int egnn_patch_degrees(const float* w_base, const float* rowsum_base,
+                       const float* dinv_base, const uint8_t* iso_base,
+                       const float* x0_base, int64_t n,
+                       const int32_t* delta_row_host, const int32_t* delta_col_host,
+                       const float* delta_val_host, int32_t n_delta,
+                       float* dinv_out, uint8_t* iso_out, float* x0_out,
+                       egnn_stream_t stream);
+
+/* ---- fused Chebyshev-wavelet pass -----------------------------------------
+ * Replaces the rescale (calibration/WATS.py:55), chebyshev_polynomials
+ * (:29-37), the heat-coefficient combination (:65-68) and the row L1
+ * normalisation (:71-72).  For k = 1..K one kernel computes
+ *   T_k = m_k * L~ T_{k-1} - T_{k-2},   m_1 = 1, m_k = 2,
+ *   L~ = op_scale * L_sym + op_shift * I   (reference: 2/lambda_max = 1 and -1),
+ *   (L~ x)_i = theta_i x_i - op_scale dinv_i sum_{j != i} a_ij dinv_j x_j,
+ *   theta_i = op_scale (1 - iso_i) + op_shift,
+ * and accumulates out[i, s, :] += coeffs_host[s*(K+1)+k] * T_k[i, :] for all
+ * n_scales scales in the same pass; the last order applies the L1
+ * normalisation per (row, scale) when normalize_l1 != 0.
+ *   x0            [n, f]        input signal T_0
+ *   out           [n, n_scales, f]
+ *   t_all_or_null [K+1, n, f]   when non-NULL every order is also stored
+ *   delta_*       optional edge flips applied on top of the CSR (UGCA
+ *                 recompute): entry e adds delta_val[e] to
+ *                 A[delta_row[e], delta_col[e]]; dinv/iso/x0 passed in must
+ *                 already describe the perturbed graph (egnn_patch_degrees).
+ *                 Host pointers, n_delta <= EGNN_MAX_DELTA.
+ * workspace: egnn_cheb_workspace_bytes(n, f) bytes, 256-byte aligned.
+ * order_events_host: NULL, or 2*K cudaEvent_t handles; events 2(k-1) and
+ * 2(k-1)+1 are recorded on `stream` around order k's kernel (per-kernel
+ * timing for the roofline report; no effect on results).                    */
+size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f);
+int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx,
+                      const float* vals_or_null, const float* dinv,
+                      const uint8_t* iso, const float* x0, int64_t n, int64_t nnz,
+                      int32_t f, int32_t k, int32_t n_scales,
+                      const float* coeffs_host, float op_scale, float op_shift,
+                      float* out, float* t_all_or_null, int32_t normalize_l1,
+                      const int32_t* delta_row_host, const int32_t* delta_col_host,
+                      const float* delta_val_host, int32_t n_delta,
+                      void* workspace, size_t workspace_bytes,
+                      egnn_stream_t stream, void* const* order_events_host);
+
+/* ---- row-sharded variant (1-D partition) -------------------------
+ * One order on the rows [row_begin, row_end) this rank owns; new in this
+ * build (the reference is single-device).  t_prev_full is the exchanged
+ * [n, f] T_{k-1}; t_prev_local / t_prev2_local / t_out_local / out_local are
+ * the rank's own [rows, f] / [rows, n_scales, f] slabs.  `phase` selects the
+ * half of the column-split CSR:
+ *   0 = local columns only: partial sums -> acc_ws (runs while the exchange
+ *       of T_{k-1} is in flight; gathers touch t_prev_local only),
+ *   1 = remote columns + acc_ws, then the fused epilogue,
+ *   2 = the unsplit rows in one launch (rowptr_local/colidx_local = full CSR
+ *       of the rank's rows).
+ * nnz_hint sizes the lane layout (mean row length of the launched half).    */
+int egnn_cheb_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_local,
+                            const int32_t* rowptr_remote, const int32_t* colidx_remote,
+                            const float* dinv_full, const uint8_t* iso_full,
+                            const float* t_prev_full, const float* t_prev_local,
+                            const float* t_prev2_local, float* t_out_local,
+                            float* out_local, float* acc_ws,
+                            int64_t n, int64_t nnz_hint, int64_t row_begin, int64_t row_end,
+                            int32_t f, int32_t order, int32_t k_max, int32_t n_scales,
+                            const float* coeffs_host, float op_scale, float op_shift,
+                            int32_t normalize_l1, int32_t phase,
+                            egnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGNN_B200_H */

@@ -1,0 +1,262 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the
+reference-generated golden vectors.  Tolerances (SURVEY 8c / north_star):
+per order k and for S: ||gpu - ref||_inf / ||ref||_inf <= 1e-5 and, element
+wise, |delta| <= 1e-5 * max(|ref|, 1e-3 ||ref||_inf); H (after the float32
+cast) within 1e-6 absolute with exact sign agreement."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import efficient_gnn_b200 as egnn
+from efficient_gnn_b200 import synth
+from oracle import wats_oracle as orc
+from helpers import FEATURE_CASES, elementwise_ok, load_case, rel_max_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def check_parts(res, ref_T, ref_S, ref_H, tag=""):
+    worst = []
+    for i, (got, ref) in enumerate(zip(res.orders, ref_T)):
+        g = got.cpu().numpy()
+        err = rel_max_err(g, ref)
+        worst.append(err)
+        assert err <= TOL, f"{tag} order {i}: rel max err {err:.3e}"
+        assert elementwise_ok(g, ref, TOL), f"{tag} order {i}: element-wise bound"
+    for j, rs in enumerate(ref_S):
+        g = res.combined[:, j, :].cpu().numpy()
+        assert rel_max_err(g, rs) <= TOL, f"{tag} S[{j}]"
+        assert elementwise_ok(g, rs, TOL)
+    f = ref_H[0].shape[1]
+    for j, rh in enumerate(ref_H):
+        g = res.features[:, j * f:(j + 1) * f].cpu().numpy()
+        rh32 = rh.astype(np.float32)
+        sure = np.abs(ref_S[j]) > 1e-4 * np.abs(ref_S[j]).max()      # away from sign flips of S ~ 0
+        np.testing.assert_allclose(g[sure], rh32[sure], rtol=0, atol=1e-6 if f == 1 else 2e-5)
+        assert np.array_equal(np.sign(g[sure]), np.sign(rh32[sure]))
+    return worst
+
+
+@pytest.mark.parametrize("name", FEATURE_CASES)
+def test_golden_case(name):
+    c = load_case(name)
+    x0 = torch.from_numpy(c["X0"]) if c["custom_x0"] else None
+    res = egnn.graph_wavelet_features(c["adj"], k=c["k"], s=c["s"], X0=x0, return_parts=True)
+    growth = check_parts(res, c["T"], [c["S"]], [c["H"]], name)
+    print(f"\n[{name}] per-order rel err: " + " ".join(f"{e:.2e}" for e in growth))
+    # the fused (normalising, no stored orders) pass must agree with the parts pass
+    fused = egnn.graph_wavelet_features(c["adj"], k=c["k"], s=c["s"], X0=x0)
+    sure = np.abs(c["S"]) > 1e-4 * np.abs(c["S"]).max()
+    np.testing.assert_allclose(fused.cpu().numpy()[sure], c["H"].astype(np.float32)[sure], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["kat_path", "cora_noloop", "cora_loops", "directed_weighted"])
+def test_degree_vectors(name):
+    c = load_case(name)
+    g = egnn.CsrGraph.from_scipy(c["adj"])
+    _r, _c, _v, w, iso = orc.normalized_laplacian_parts(c["adj"])
+    assert np.array_equal(g.iso.cpu().numpy().astype(bool), iso)
+    np.testing.assert_allclose(g.dinv.cpu().numpy(), 1.0 / w.astype(np.float64), rtol=2e-7)
+    x0 = orc.input_signal(c["adj"]).ravel()
+    if name == "directed_weighted":      # float32 row sums: order of summation differs
+        np.testing.assert_allclose(g.x0.cpu().numpy(), x0, rtol=1e-6)
+    else:
+        np.testing.assert_allclose(g.x0.cpu().numpy(), x0, rtol=0, atol=0 if name == "kat_path" else 3e-7)
+
+
+@pytest.mark.parametrize("n,density,weighted", [(1, 1.0, False), (5, 0.5, False), (257, 0.05, False),
+                                                 (1000, 0.01, True), (2708, 0.002, False), (130, 0.0, False)])
+def test_dense_to_csr_bit_exact(n, density, weighted):
+    rng = np.random.default_rng(n)
+    dense = (rng.random((n, n)) < density).astype(np.float32)
+    if weighted:
+        dense *= rng.uniform(0.5, 2.0, (n, n)).astype(np.float32)
+    ref = sp.csr_matrix(dense)
+    g = egnn.CsrGraph.from_dense(torch.from_numpy(dense).cuda())
+    assert g.nnz == ref.nnz
+    assert np.array_equal(g.rowptr.cpu().numpy(), ref.indptr)
+    assert np.array_equal(g.colidx.cpu().numpy(), ref.indices)
+    if weighted:
+        assert np.array_equal(g.vals.cpu().numpy(), ref.data)
+    else:
+        assert g.vals is None
+    # non-contiguous rows (a view with a larger stride) take the scalar path
+    if n > 4:
+        big = torch.zeros(n, n + 3, device="cuda")
+        big[:, :n] = torch.from_numpy(dense).cuda()
+        g2 = egnn.CsrGraph.from_dense(big[:, :n])
+        assert np.array_equal(g2.colidx.cpu().numpy(), ref.indices)
+
+
+def test_dense_entry_point_equals_sparse_entry_point():
+    c = load_case("cora_loops")
+    dense = torch.tensor(c["adj"].toarray(), dtype=torch.float32).cuda()
+    a = egnn.graph_wavelet_features(dense)
+    b = egnn.graph_wavelet_features(c["adj"])
+    assert torch.equal(a, b)
+    assert a.shape == (c["n"], 1) and a.dtype == torch.float32 and a.is_cuda
+
+
+def test_reference_function_bodies_run_on_the_operator():
+    """(2/2.0)*L - identity(N), L @ X and 2*L @ X: the algebra of
+    calibration/WATS.py:34,36,55 works on the implicit operator."""
+    from scipy.sparse import identity
+    c = load_case("cora_noloop")
+    n = c["n"]
+    L = egnn.compute_normalized_laplacian(c["adj"])
+    L_rescaled = (2 / 2.0) * L - identity(n)
+    orders = egnn.chebyshev_polynomials(L_rescaled, 3, c["X0"])
+    assert len(orders) == 4
+    for got, ref in zip(orders, c["T"]):
+        assert rel_max_err(got.cpu().numpy(), ref) <= TOL
+    x0 = torch.from_numpy(c["X0"]).cuda()
+    t1 = L_rescaled @ x0
+    assert rel_max_err(t1.cpu().numpy(), c["T"][1]) <= TOL
+    t2 = 2 * L_rescaled @ t1 - x0
+    assert rel_max_err(t2.cpu().numpy(), c["T"][2]) <= 2 * TOL
+    lap = orc.rescaled_laplacian(c["adj"]) + identity(n)          # L_sym itself
+    y = L @ x0
+    assert rel_max_err(y.cpu().numpy(), lap @ c["X0"].astype(np.float64)) <= TOL
+
+
+def test_multi_scale_single_pass():
+    c = load_case("cora_loops")
+    scales = [0.4, 0.8, 1.6, 3.2]
+    res = egnn.graph_wavelet_features(c["adj"], k=3, s=scales, return_parts=True)
+    p = orc.wavelet_parts(c["adj"], k=3, s=scales)
+    check_parts(res, p["T"], p["S"], p["H"], "multi-scale")
+    feats = egnn.graph_wavelet_features(c["adj"], k=3, s=scales)
+    assert feats.shape == (c["n"], 4)
+    one = egnn.graph_wavelet_features(c["adj"], k=3, s=0.8)
+    assert torch.equal(feats[:, 1:2], one)
+
+
+@pytest.mark.parametrize("f", [1, 2, 3, 4, 8, 20, 33, 64, 128, 130, 260])
+def test_feature_widths(f):
+    c = load_case("cora_noloop")
+    rng = np.random.default_rng(f)
+    x0 = rng.standard_normal((c["n"], f)).astype(np.float32)
+    res = egnn.graph_wavelet_features(c["adj"], k=4, s=[0.8, 1.6], X0=torch.from_numpy(x0), return_parts=True)
+    p = orc.wavelet_parts(c["adj"], k=4, s=[0.8, 1.6], x0=x0)
+    check_parts(res, p["T"], p["S"], p["H"], f"F={f}")
+    fused = egnn.graph_wavelet_features(c["adj"], k=4, s=[0.8, 1.6], X0=torch.from_numpy(x0))
+    np.testing.assert_allclose(fused.cpu().numpy(), np.concatenate(p["H"], axis=1), rtol=0, atol=3e-5)
+
+
+@pytest.mark.parametrize("lam", [1.5, 2.0, 2.7])
+def test_lambda_max(lam):
+    c = load_case("cora_loops")
+    res = egnn.graph_wavelet_features(c["adj"], k=3, s=0.8, lambda_max=lam, return_parts=True)
+    p = orc.wavelet_parts(c["adj"], k=3, s=0.8, lambda_max=lam)
+    check_parts(res, p["T"], p["S"], p["H"], f"lambda={lam}")
+
+
+@pytest.mark.parametrize("shape,f,loops", [("pubmed", 1, True), ("physics", 1, False), ("physics", 16, True),
+                                           ("arxiv", 1, True), ("arxiv", 8, False)])
+def test_named_shapes_against_oracle(shape, f, loops):
+    rp, ci, n = synth.synth_csr(shape, self_loops=loops)
+    adj = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
+    x0 = None
+    if f > 1:
+        x0 = np.random.default_rng(3).standard_normal((n, f)).astype(np.float32)
+    g = egnn.CsrGraph(rp.cuda(), ci.cuda(), None, n)
+    res = egnn.graph_wavelet_features(g, k=3, s=0.8, X0=None if x0 is None else torch.from_numpy(x0),
+                                      return_parts=True)
+    p = orc.wavelet_parts(adj, k=3, s=0.8, x0=x0)
+    errs = check_parts(res, p["T"], p["S"], p["H"], f"{shape} F={f}")
+    print(f"\n[{shape} F={f}] per-order rel err: " + " ".join(f"{e:.2e}" for e in errs))
+
+
+def test_edge_flip_deltas_match_rebuilt_graph():
+    """UGCA recompute: base CSR + <= 2*budget flips == features of the rebuilt
+    perturbed graph (and of the oracle on it)."""
+    c = load_case("cora_loops")
+    n = c["n"]
+    dense = c["adj"].toarray()
+    rng = np.random.default_rng(5)
+    target = 17
+    rows, cols, vals = [], [], []
+    others = rng.choice(np.setdiff1d(np.arange(n), [target]), 5, replace=False)
+    # make sure at least one flip removes an existing edge
+    nbrs = np.nonzero(dense[target])[0]
+    nbrs = nbrs[nbrs != target]
+    if len(nbrs):
+        others[0] = nbrs[0]
+    pert = dense.copy()
+    for j in others:
+        v = -2 * dense[target, j] + 1            # calib_fga.py:897-904
+        pert[target, j] += v
+        pert[j, target] += v
+        rows += [target, int(j)]
+        cols += [int(j), target]
+        vals += [float(v), float(v)]
+    g = egnn.CsrGraph.from_scipy(c["adj"])
+    res_d = egnn.graph_wavelet_features(g, deltas=(rows, cols, vals), return_parts=True)
+    p = orc.wavelet_parts(sp.csr_matrix(pert.astype(np.float32)))
+    check_parts(res_d, p["T"], p["S"], p["H"], "delta")
+    res_r = egnn.graph_wavelet_features(torch.from_numpy(pert.astype(np.float32)).cuda(), return_parts=True)
+    for a, b in zip(res_d.orders, res_r.orders):
+        assert rel_max_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-6
+    # the untouched graph is unchanged by an empty delta list
+    assert torch.equal(egnn.graph_wavelet_features(g, deltas=([], [], [])), egnn.graph_wavelet_features(g))
+
+
+def test_isolating_flip_updates_iso():
+    a = np.zeros((6, 6), np.float32)
+    a[0, 1] = a[1, 0] = 1
+    a[2, 3] = a[3, 2] = a[3, 4] = a[4, 3] = 1
+    g = egnn.CsrGraph.from_scipy(sp.csr_matrix(a))
+    rows, cols, vals = [0, 1], [1, 0], [-1.0, -1.0]       # removes the only edge of nodes 0 and 1
+    res = egnn.graph_wavelet_features(g, deltas=(rows, cols, vals), return_parts=True)
+    b = a.copy()
+    b[0, 1] = b[1, 0] = 0
+    p = orc.wavelet_parts(sp.csr_matrix(b))
+    for got, ref in zip(res.orders, p["T"]):
+        np.testing.assert_allclose(got.cpu().numpy(), ref, atol=1e-6)
+
+
+def test_empty_and_degenerate_inputs():
+    # no edges at all: every node isolated -> L~ = -I, T_k = (-1)^k X0, X0 = log1p(0) = 0
+    g = egnn.CsrGraph(torch.zeros(8, dtype=torch.int32, device="cuda"),
+                      torch.zeros(0, dtype=torch.int32, device="cuda"), None, 7)
+    f = egnn.graph_wavelet_features(g)
+    assert f.shape == (7, 1) and torch.count_nonzero(f) == 0
+    x0 = torch.arange(7, dtype=torch.float32).reshape(7, 1) + 1
+    res = egnn.graph_wavelet_features(g, k=3, X0=x0, return_parts=True)
+    for i, t in enumerate(res.orders):
+        np.testing.assert_allclose(t.cpu().numpy(), ((-1) ** i) * x0.numpy(), atol=1e-6)
+    # single node with a self loop
+    g1 = egnn.CsrGraph.from_dense(torch.ones(1, 1, device="cuda"))
+    f1 = egnn.graph_wavelet_features(g1)
+    p1 = orc.wavelet_parts(sp.csr_matrix(np.ones((1, 1), np.float32)))
+    np.testing.assert_allclose(f1.cpu().numpy(), p1["H"][0], atol=1e-6)
+
+
+def test_hub_row_accuracy():
+    """A star: one row with 50k entries (float32 accumulation on a long row)."""
+    n = 50_001
+    hub = np.zeros(n - 1, dtype=np.int64)
+    leaves = np.arange(1, n, dtype=np.int64)
+    rows = np.concatenate([hub, leaves])
+    cols = np.concatenate([leaves, hub])
+    adj = sp.csr_matrix((np.ones(rows.size, np.float32), (rows, cols)), shape=(n, n))
+    x0 = np.random.default_rng(0).uniform(0.5, 1.5, (n, 4)).astype(np.float32)
+    res = egnn.graph_wavelet_features(adj, k=3, X0=torch.from_numpy(x0), return_parts=True)
+    p = orc.wavelet_parts(adj, k=3, x0=x0)
+    check_parts(res, p["T"], p["S"], p["H"], "star")
+
+
+def test_errors_are_exceptions():
+    c = load_case("kat_path")
+    g = egnn.CsrGraph.from_scipy(c["adj"])
+    with pytest.raises(ValueError):
+        egnn.graph_wavelet_features(g, X0=torch.zeros(3, 1))
+    with pytest.raises(egnn.EgnnError):
+        egnn.graph_wavelet_features(g, s=list(np.linspace(0.1, 1, 9)))      # > EGNN_MAX_SCALES
+    with pytest.raises(egnn.EgnnError):
+        egnn.graph_wavelet_features(g, deltas=([9], [0], [1.0]))             # index out of range
+    with pytest.raises(TypeError):
+        egnn.chebyshev_polynomials(c["lt"], 3, c["X0"])

@@ -1,0 +1,87 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's full sizes
+(the oracle would need minutes there).  For a symmetric graph L~ = L_sym - I
+has the eigenpair (-1, sqrt(w)), so T_k(L~) sqrt(w) = (-1)^k sqrt(w); the
+operator is linear and symmetric (<v, L~ x> = <L~ v, x>)."""
+import numpy as np
+import pytest
+import torch
+
+import efficient_gnn_b200 as egnn
+from efficient_gnn_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=["arxiv", "reddit"])
+def big_graph(request):
+    rp, ci, n = synth.synth_csr(request.param, self_loops=True, device="cuda")
+    g = egnn.CsrGraph(rp, ci, None, n)
+    return request.param, g
+
+
+def test_eigenvector_orders(big_graph):
+    name, g = big_graph
+    v = torch.sqrt(g.w).reshape(-1, 1)
+    for f in (1, 4):
+        x0 = v * torch.arange(1, f + 1, device="cuda", dtype=torch.float32)
+        res = egnn.graph_wavelet_features(g, k=5, X0=x0, return_parts=True)
+        scale = x0.abs().max().item()
+        for i, t in enumerate(res.orders):
+            err = (t - ((-1) ** i) * x0).abs().max().item() / scale
+            assert err <= 1e-5, f"{name} F={f} order {i}: {err:.2e}"
+
+
+def test_linearity_and_symmetry(big_graph):
+    name, g = big_graph
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(g.n, 2, generator=gen, device="cuda")
+    y = torch.randn(g.n, 2, generator=gen, device="cuda")
+    sx = egnn.graph_wavelet_features(g, k=3, s=[0.8, 1.6], X0=x, return_parts=True).combined
+    sy = egnn.graph_wavelet_features(g, k=3, s=[0.8, 1.6], X0=y, return_parts=True).combined
+    sxy = egnn.graph_wavelet_features(g, k=3, s=[0.8, 1.6], X0=2 * x - 3 * y, return_parts=True).combined
+    ref = 2 * sx - 3 * sy
+    assert ((sxy - ref).abs().max() / ref.abs().max()).item() <= 2e-5
+    L = egnn.compute_normalized_laplacian(g).rescaled(2.0)
+    lx, ly = (L @ x).double(), (L @ y).double()
+    a = (y.double() * lx).sum().item()
+    b = (ly * x.double()).sum().item()
+    assert abs(a - b) <= 1e-4 * max(1.0, abs(a))
+
+
+def test_default_features_are_signs_and_degree_signal(big_graph):
+    name, g = big_graph
+    deg = (g.rowptr[1:] - g.rowptr[:-1]).double()
+    assert torch.allclose(g.x0.double(), torch.log1p(deg), rtol=2e-7, atol=0)
+    assert torch.equal(g.rowsum.double(), deg)
+    f = egnn.graph_wavelet_features(g)
+    assert f.shape == (g.n, 1)
+    assert bool(((f.abs() - 1).abs() < 1e-6).logical_or(f == 0).all())   # F=1: H = sign(S)
+    again = egnn.graph_wavelet_features(g)
+    assert torch.equal(f, again)                                        # deterministic
+
+
+def test_delta_recompute_equals_rebuild_at_scale(big_graph):
+    name, g = big_graph
+    if name != "arxiv":
+        pytest.skip("rebuild comparison only at arxiv size")
+    target = 123
+    others = [5, 77, 4096, 99_999, 150_000]
+    start, end = int(g.rowptr[target]), int(g.rowptr[target + 1])
+    nbrs = set(g.colidx[start:end].tolist())
+    rows, cols, vals = [], [], []
+    ei_r = torch.repeat_interleave(torch.arange(g.n, device="cuda"), (g.rowptr[1:] - g.rowptr[:-1]).long())
+    keys = ei_r * g.n + g.colidx.long()
+    add_keys, drop_keys = [], []
+    for j in others:
+        v = -1.0 if j in nbrs else 1.0
+        rows += [target, j]
+        cols += [j, target]
+        vals += [v, v]
+        (drop_keys if v < 0 else add_keys).extend([target * g.n + j, j * g.n + target])
+    keep = ~torch.isin(keys, torch.tensor(drop_keys, device="cuda", dtype=torch.long))
+    new_keys = torch.cat([keys[keep], torch.tensor(add_keys, device="cuda", dtype=torch.long)])
+    g2 = egnn.CsrGraph.from_edge_index(torch.stack([new_keys // g.n, new_keys % g.n]), g.n)
+    a = egnn.graph_wavelet_features(g, deltas=(rows, cols, vals), return_parts=True)
+    b = egnn.graph_wavelet_features(g2, return_parts=True)
+    for ta, tb in zip(a.orders, b.orders):
+        assert ((ta - tb).abs().max() / tb.abs().max()).item() <= 2e-6

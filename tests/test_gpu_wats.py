@@ -1,0 +1,76 @@
+"""Downstream parity: the WATS calibrator built on CUDA features vs the same
+class fed oracle features, same device, same seed -> accuracy / class-wise ECE
+/ mean confidence identical to 4 decimals (north_star)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import efficient_gnn_b200 as egnn
+from efficient_gnn_b200 import synth
+from oracle import wats_oracle as orc
+from models_for_tests import DenseGCN, FixedLogits
+
+pytestmark = pytest.mark.gpu
+
+
+def run(shape, self_loops, use_gcn, override):
+    sh = synth.SHAPES[shape]
+    rp, ci, n = synth.synth_csr(shape, self_loops=self_loops)
+    adj_csr = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
+    adj = torch.tensor(adj_csr.toarray(), dtype=torch.float32)
+    y, logits, val, test = synth.synth_labels(sh.n, sh.n_classes, seed=42)
+    x = torch.randn(sh.n, 16, generator=torch.Generator().manual_seed(7))
+    feats = orc.wavelet_features(adj_csr).astype(np.float32) if override else None
+    torch.manual_seed(42)
+    torch.cuda.manual_seed_all(42)
+    np.random.seed(42)
+    base = DenseGCN(16, sh.n_classes) if use_gcn else FixedLogits(logits)
+    cal = egnn.WATS(base, x, y, adj, val, verbose=False, _features_override=feats)
+    cal.eval()
+    with torch.no_grad():
+        lp = cal(x, adj).cpu().numpy()
+    return cal, orc.evaluate_probs(lp, y.numpy(), test.numpy()), adj_csr
+
+
+@pytest.mark.parametrize("shape,self_loops,use_gcn", [("cora", False, False), ("cora", True, True),
+                                                      ("pubmed", True, False)])
+def test_downstream_identical_to_4_decimals(shape, self_loops, use_gcn):
+    cal_gpu, m_gpu, adj_csr = run(shape, self_loops, use_gcn, override=False)
+    cal_ref, m_ref, _ = run(shape, self_loops, use_gcn, override=True)
+    assert cal_gpu.graph is not None and cal_gpu.wavelet_feats.is_cuda
+    assert "wavelet_feats" not in cal_gpu.state_dict()
+    # features: float32, identical up to the last bit of 1.0 (H = sign(S) for F = 1)
+    np.testing.assert_allclose(cal_gpu.wavelet_feats.cpu().numpy(), cal_ref.wavelet_feats.cpu().numpy(),
+                               rtol=0, atol=1e-6)
+    for a, b, what in zip(m_gpu, m_ref, ("accuracy", "confidence", "ece")):
+        assert round(a, 4) == round(b, 4), f"{what}: {a} vs {b}"
+
+
+def test_recompute_on_forward_and_deltas():
+    sh = synth.SHAPES["cora"]
+    rp, ci, n = synth.synth_csr("cora", self_loops=True)
+    adj_csr = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
+    adj = torch.tensor(adj_csr.toarray(), dtype=torch.float32).cuda()
+    y, logits, val, test = synth.synth_labels(sh.n, sh.n_classes, seed=42)
+    x = torch.zeros(n, 4)
+    torch.manual_seed(0)
+    cal = egnn.WATS(FixedLogits(logits), x, y, adj, val, verbose=False, s=[0.4, 0.8], k=3)
+    assert cal.wavelet_feats.shape == (n, 2)
+    cal.eval()
+    target, j = 10, 2000
+    v = float(-2 * adj[target, j].item() + 1)
+    pert = adj.clone()
+    pert[target, j] += v
+    pert[j, target] += v
+    with torch.no_grad():
+        cached = cal(x, pert)                      # reference behaviour: features stay cached
+        base = cal(x, adj)
+        assert torch.equal(cached, base)           # FixedLogits ignores adj
+        by_delta = cal(x, pert, deltas=([target, j], [j, target], [v, v]))
+        cal.recompute_on_forward = True
+        by_dense = cal(x, pert)
+    assert torch.allclose(by_delta, by_dense, atol=1e-5)
+    want = orc.wavelet_features(sp.csr_matrix(pert.cpu().numpy()), k=3, s=[0.4, 0.8]).astype(np.float32)
+    got = cal.features_for(pert).cpu().numpy()
+    np.testing.assert_allclose(got, want, atol=1e-6)
