@@ -23,15 +23,27 @@ SYMBOLS = {
     "egnn_device_info": (C.c_int, [_P, _P, _P]),
     "egnn_dense_to_csr_count": (C.c_int, [_P, _I64, _I64, _P, _P, _P]),
     "egnn_dense_to_csr_fill": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P]),
-    "egnn_graph_prep": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "egnn_graph_prep": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "egnn_sell_geometry": (C.c_int, [_I64, _I64, _P, _P, _P]),
+    "egnn_sell_ws_bytes": (_SZ, [_I64, _I64, _I32, _I32]),
+    "egnn_sell_prepare": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _SZ, _P]),
+    "egnn_sell_fill": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _SZ, _P]),
     "egnn_patch_degrees": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "egnn_cheb_workspace_bytes": (_SZ, [_I64, _I32]),
     "egnn_cheb_wavelet": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, _F32, _F32,
-                                    _P, _P, _I32, _P, _P, _P, _I32, _P, _SZ, _P, _P]),
+                                    _P, _P, _I32, _P, _P, _P, _I32, _P, _SZ, _P, _P, _P]),
     "egnn_cheb_order_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                           _I64, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _P, _F32, _F32,
                                           _I32, _I32, _P]),
 }
+
+
+class SellPlanStruct(C.Structure):
+    """Mirror of ``egnn_sell_plan`` (include/egnn_b200.h)."""
+    _fields_ = [("n", C.c_int32), ("n_blocks", C.c_int32), ("col_block", C.c_int32), ("lmax", C.c_int32),
+                ("n_slices", C.c_int64), ("n_vrows", C.c_int64), ("n_entries", C.c_int64), ("n_rowv", C.c_int64),
+                ("slice_off", C.c_void_p), ("blk_slice_ptr", C.c_void_p), ("idx", C.c_void_p),
+                ("rv_ptr", C.c_void_p), ("rv_idx", C.c_void_p), ("vpart", C.c_void_p)]
 
 
 class EgnnError(RuntimeError):

@@ -6,6 +6,7 @@
 #include "cheb.cuh"
 #include "common.cuh"
 #include "prep.cuh"
+#include "sell.cuh"
 
 namespace egnn {
 
@@ -93,6 +94,82 @@ static int grid_for(int64_t work_items, int threads) {
     return (int)b;
 }
 
+
+// ---- SELL plan workspace layout (shared by prepare and fill) -----------------
+struct SellWs {
+    int32_t *seg_start, *seg_cnt, *nv, *u_off, *nvrow, *rv_ptr, *uval, *perm, *vsrc, *vslot, *vrow;
+    uint32_t *key, *key_sorted;
+    int32_t *q_ptr, *vp_ptr, *bsp, *slice_sz, *slice_off;
+    int64_t* totals;
+    void* cub_temp;
+    size_t cub_bytes;
+    size_t total_bytes;
+    int64_t umax, smax;
+};
+
+static size_t sell_cub_bytes(int64_t cn1, int64_t n1, int64_t umax, int64_t smax1) {
+    size_t a = 0, b = 0, c = 0, d = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, a, (int32_t*)nullptr, (int32_t*)nullptr, (int)cn1);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (int32_t*)nullptr, (int32_t*)nullptr, (int)n1);
+    cub::DeviceScan::ExclusiveSum(nullptr, c, (int32_t*)nullptr, (int32_t*)nullptr, (int)smax1);
+    cub::DeviceRadixSort::SortPairs(nullptr, d, (uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int)umax);
+    size_t m = a > b ? a : b;
+    m = m > c ? m : c;
+    m = m > d ? m : d;
+    return m + 256;
+}
+
+static SellWs sell_ws_layout(void* base, int64_t n, int64_t nnz, int C, int lmax) {
+    SellWs w{};
+    const int64_t cn = (int64_t)C * n;
+    w.umax = cn + nnz / lmax + 1;
+    w.smax = (w.umax + (int64_t)kSellSliceRows * C) / kSellSliceRows + 1;
+    size_t off = 0;
+    char* b = (char*)align_up((size_t)base, 256);
+    auto take = [&](size_t bytes) { void* ptr = b + off; off += align_up(bytes, 256); return ptr; };
+    w.seg_start = (int32_t*)take(4 * cn);
+    w.seg_cnt = (int32_t*)take(4 * cn);
+    w.nv = (int32_t*)take(4 * (cn + 1));
+    w.u_off = (int32_t*)take(4 * (cn + 1));
+    w.nvrow = (int32_t*)take(4 * (n + 1));
+    w.rv_ptr = (int32_t*)take(4 * (n + 1));
+    w.key = (uint32_t*)take(4 * w.umax);
+    w.key_sorted = (uint32_t*)take(4 * w.umax);
+    w.uval = (int32_t*)take(4 * w.umax);
+    w.perm = (int32_t*)take(4 * w.umax);
+    w.vsrc = (int32_t*)take(4 * w.umax);
+    w.vslot = (int32_t*)take(4 * w.umax);
+    w.vrow = (int32_t*)take(4 * w.umax);
+    w.q_ptr = (int32_t*)take(4 * (C + 1));
+    w.vp_ptr = (int32_t*)take(4 * (C + 1));
+    w.bsp = (int32_t*)take(4 * (C + 1));
+    w.slice_sz = (int32_t*)take(4 * (w.smax + 1));
+    w.slice_off = (int32_t*)take(4 * (w.smax + 1));
+    w.totals = (int64_t*)take(8 * 8);
+    w.cub_bytes = sell_cub_bytes(cn + 1, n + 1, w.umax, w.smax + 1);
+    w.cub_temp = take(w.cub_bytes);
+    w.total_bytes = off + 256;
+    return w;
+}
+
+static int sell_check_geometry(int64_t n, int64_t nnz, const egnn_sell_plan* plan) {
+    EGNN_REQUIRE(plan != nullptr, "null plan");
+    EGNN_REQUIRE(n >= 1 && n < (int64_t(1) << 31) && nnz >= 0 && nnz < (int64_t(1) << 31), "n/nnz out of range");
+    EGNN_REQUIRE(plan->n_blocks >= 1 && plan->n_blocks <= kSellMaxBlocks, "n_blocks out of range");
+    EGNN_REQUIRE(plan->col_block >= 1 && plan->col_block <= 65535, "col_block must fit 16-bit local indices");
+    EGNN_REQUIRE((int64_t)plan->col_block * plan->n_blocks >= n, "column blocks do not cover n");
+    EGNN_REQUIRE(plan->lmax >= 8 && plan->lmax <= 65536 && plan->lmax % 8 == 0, "lmax must be a multiple of 8 in [8, 65536]");
+    EGNN_REQUIRE((int64_t)plan->n_blocks * n < (int64_t(1) << 30), "n_blocks * n too large");
+    return EGNN_OK;
+}
+
+static int device_sm_count() {
+    int dev = 0, sms = kSmCountB200;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
 }  // namespace egnn
 
 using namespace egnn;
@@ -150,18 +227,25 @@ int egnn_dense_to_csr_fill(const float* adj, int64_t n, int64_t ld, const int32_
 
 int egnn_graph_prep(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null, int64_t n,
                     float* dinv, uint8_t* iso, float* x0_logdeg, float* w_out_or_null,
-                    float* rowsum_out, float* diag_ws, double* colsum_ws, egnn_stream_t stream) {
+                    float* rowsum_out, float* diag_ws, double* colsum_ws, int32_t* unsorted_flag_or_null,
+                    egnn_stream_t stream) {
     EGNN_REQUIRE(rowptr && dinv && iso && rowsum_out && diag_ws && colsum_ws, "null pointer");
     EGNN_REQUIRE(n >= 0, "bad shape");
     if (n == 0) return EGNN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_cuda(cudaMemsetAsync(colsum_ws, 0, sizeof(double) * n, st), "memset colsum");
     if (rc) return rc;
+    if (unsorted_flag_or_null) {
+        rc = check_cuda(cudaMemsetAsync(unsorted_flag_or_null, 0, sizeof(int32_t), st), "memset flag");
+        if (rc) return rc;
+    }
     const int g = grid_for(n * 32, 256);
     if (vals_or_null)
-        degree_kernel<true><<<g, 256, 0, st>>>(rowptr, colidx, vals_or_null, n, rowsum_out, diag_ws, colsum_ws);
+        degree_kernel<true><<<g, 256, 0, st>>>(rowptr, colidx, vals_or_null, n, rowsum_out, diag_ws, colsum_ws,
+                                               unsorted_flag_or_null);
     else
-        degree_kernel<false><<<g, 256, 0, st>>>(rowptr, colidx, nullptr, n, rowsum_out, diag_ws, colsum_ws);
+        degree_kernel<false><<<g, 256, 0, st>>>(rowptr, colidx, nullptr, n, rowsum_out, diag_ws, colsum_ws,
+                                                unsorted_flag_or_null);
     EGNN_LAUNCH_CHECK("degree_kernel launch");
     normaliser_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(colsum_ws, diag_ws, rowsum_out, n, dinv, iso,
                                                                    x0_logdeg, w_out_or_null);
@@ -207,7 +291,8 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
                       float* out, float* t_all_or_null, int32_t normalize_l1,
                       const int32_t* delta_row_host, const int32_t* delta_col_host,
                       const float* delta_val_host, int32_t n_delta, void* workspace,
-                      size_t workspace_bytes, egnn_stream_t stream, void* const* order_events_host) {
+                      size_t workspace_bytes, egnn_stream_t stream, void* const* order_events_host,
+                      const egnn_sell_plan* sell_plan) {
     EGNN_REQUIRE(rowptr && dinv && iso && x0 && out && coeffs_host, "null pointer");
     EGNN_REQUIRE(nnz == 0 || colidx, "null colidx");
     EGNN_REQUIRE(n >= 0 && n < (int64_t(1) << 31) && nnz >= 0 && nnz < (int64_t(1) << 31), "n/nnz out of int32 range");
@@ -258,6 +343,60 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
     if (cfg.prescaled) {
         prescale_kernel<<<grid_for((int64_t)slab_elems, 256), 256, 0, st>>>(x0, dinv, ybuf[0], n, f, 0);
         EGNN_LAUNCH_CHECK("prescale_kernel launch");
+    }
+
+    if (sell_plan) {
+        EGNN_REQUIRE(f == 1 && vals_or_null == nullptr, "the SELL plan serves F = 1 on a binary adjacency");
+        EGNN_REQUIRE(sell_plan->n == n && sell_plan->vpart && sell_plan->slice_off && sell_plan->blk_slice_ptr &&
+                     sell_plan->rv_ptr, "SELL plan does not match the graph or is not filled");
+        SellEpilogueParams ep{};
+        ep.delta = p.delta;
+        ep.rv_ptr = sell_plan->rv_ptr; ep.rv_idx = sell_plan->rv_idx; ep.vpart = sell_plan->vpart;
+        ep.dinv = dinv; ep.iso = iso; ep.out = out; ep.n = (int32_t)n; ep.S = n_scales;
+        ep.a = op_scale; ep.b = op_shift;
+        const size_t smem = sizeof(float) * ((size_t)sell_plan->col_block + 1);
+        rc = check_cuda(cudaFuncSetAttribute(sell_spmv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        "cudaFuncSetAttribute(sell_spmv_kernel)");
+        if (rc) return rc;
+        const int n_cta = device_sm_count();
+        const float* t_prev = x0;
+        const float* t_prev2 = nullptr;
+        for (int order = 1; order <= k; ++order) {
+            const bool last = order == k;
+            float* t_out;
+            if (t_all_or_null) t_out = t_all_or_null + (size_t)order * slab_elems;
+            else if (last) t_out = nullptr;
+            else if (order == 1) t_out = tbuf[0];
+            else if (order == 2) t_out = tbuf[1];
+            else t_out = const_cast<float*>(t_prev2);
+            const float* y_prev = ybuf[(order - 1) & 1];
+            if (order_events_host) {
+                rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1)], st), "event record");
+                if (rc) return rc;
+            }
+            if (sell_plan->n_slices > 0) {
+                sell_spmv_kernel<4><<<n_cta, kSellThreads, smem, st>>>(
+                    sell_plan->idx, sell_plan->slice_off, sell_plan->blk_slice_ptr, sell_plan->n_blocks,
+                    sell_plan->col_block, (int)sell_plan->n_slices, y_prev, (int)n, sell_plan->vpart);
+                EGNN_LAUNCH_CHECK("sell_spmv_kernel launch");
+            }
+            if (order_events_host) {
+                rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1) + 1], st), "event record");
+                if (rc) return rc;
+            }
+            ep.y_prev = y_prev; ep.tprev = t_prev; ep.tprev2 = t_prev2; ep.tk = t_out;
+            ep.y_out = last ? nullptr : ybuf[order & 1];
+            ep.first = order == 1; ep.normalize = last && normalize_l1;
+            for (int s = 0; s < n_scales; ++s) {
+                ep.c_prev[s] = coeffs_host[s * (k + 1) + order - 1];
+                ep.c_k[s] = coeffs_host[s * (k + 1) + order];
+            }
+            sell_epilogue_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(ep);
+            EGNN_LAUNCH_CHECK("sell_epilogue_kernel launch");
+            t_prev2 = t_prev;
+            t_prev = t_out;
+        }
+        return EGNN_OK;
     }
 
     p.rowptr = rowptr; p.colidx = colidx; p.vals = vals_or_null; p.dinv = dinv; p.iso = iso;
@@ -362,6 +501,102 @@ int egnn_cheb_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
     if (last && normalize_l1 && !fuse_norm) {
         l1_normalize_kernel<<<grid_for(rows * n_scales * 32, 256), 256, 0, st>>>(out_local, rows * n_scales, f);
         EGNN_LAUNCH_CHECK("l1_normalize_kernel launch");
+    }
+    return EGNN_OK;
+}
+
+int egnn_sell_geometry(int64_t n, int64_t nnz, int32_t* n_blocks, int32_t* col_block, int32_t* lmax) {
+    EGNN_REQUIRE(n_blocks && col_block && lmax, "null pointer");
+    EGNN_REQUIRE(n >= 1, "bad shape");
+    const int64_t cb_max = 49152;                     // 192 KB of float32 operand per CTA
+    int64_t c = ceil_div64(n, cb_max);
+    int64_t cb = ceil_div64(ceil_div64(n, c), 32) * 32;
+    if (cb > 65535) cb = 65535 / 32 * 32;
+    *n_blocks = (int32_t)ceil_div64(n, cb);
+    *col_block = (int32_t)cb;
+    *lmax = 256;
+    (void)nnz;
+    return EGNN_OK;
+}
+
+size_t egnn_sell_ws_bytes(int64_t n, int64_t nnz, int32_t n_blocks, int32_t lmax) {
+    if (n < 1 || n_blocks < 1 || lmax < 8) return 0;
+    return sell_ws_layout(nullptr, n, nnz, n_blocks, lmax).total_bytes;
+}
+
+int egnn_sell_prepare(const int32_t* rowptr, const int32_t* colidx, int64_t n, int64_t nnz,
+                      egnn_sell_plan* plan, void* workspace, size_t workspace_bytes, egnn_stream_t stream) {
+    int rc = sell_check_geometry(n, nnz, plan);
+    if (rc) return rc;
+    EGNN_REQUIRE(rowptr && (colidx || nnz == 0), "null pointer");
+    const int C = plan->n_blocks, CB = plan->col_block, lmax = plan->lmax;
+    SellWs w = sell_ws_layout(workspace, n, nnz, C, lmax);
+    if (!workspace || workspace_bytes < w.total_bytes) {
+        set_error("sell workspace too small: need %zu bytes, got %zu", w.total_bytes, workspace_bytes);
+        return EGNN_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t cn = (int64_t)C * n;
+    rc = check_cuda(cudaMemsetAsync(w.nv + cn, 0, 4, st), "memset"); if (rc) return rc;
+    rc = check_cuda(cudaMemsetAsync(w.nvrow + n, 0, 4, st), "memset"); if (rc) return rc;
+    rc = check_cuda(cudaMemsetAsync(w.key, 0xff, 4 * w.umax, st), "memset"); if (rc) return rc;
+    rc = check_cuda(cudaMemsetAsync(w.slice_sz, 0, 4 * (w.smax + 1), st), "memset"); if (rc) return rc;
+    rc = check_cuda(cudaMemsetAsync(w.totals, 0, 64, st), "memset"); if (rc) return rc;
+    sell_count_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(rowptr, colidx, (int)n, C, CB, lmax, w.seg_start,
+                                                                   w.seg_cnt, w.nv, w.nvrow);
+    EGNN_LAUNCH_CHECK("sell_count_kernel launch");
+    size_t tb = w.cub_bytes;
+    rc = check_cuda(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, w.nv, w.u_off, (int)(cn + 1), st), "scan nv"); if (rc) return rc;
+    tb = w.cub_bytes;
+    rc = check_cuda(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, w.nvrow, w.rv_ptr, (int)(n + 1), st), "scan nvrow"); if (rc) return rc;
+    sell_emit_kernel<<<(unsigned)ceil_div64(cn, 256), 256, 0, st>>>((int)n, C, lmax, w.seg_start, w.seg_cnt, w.nv, w.u_off,
+                                                                   w.rv_ptr, w.key, w.uval, w.vsrc, w.vslot, w.vrow);
+    EGNN_LAUNCH_CHECK("sell_emit_kernel launch");
+    tb = w.cub_bytes;
+    rc = check_cuda(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.key, w.key_sorted, w.uval, w.perm, (int)w.umax, 0, 32, st), "sort vrows");
+    if (rc) return rc;
+    sell_blocks_kernel<<<1, 32, 0, st>>>((int)n, C, w.u_off, w.q_ptr, w.vp_ptr, w.bsp, w.totals);
+    EGNN_LAUNCH_CHECK("sell_blocks_kernel launch");
+    sell_slice_kernel<<<(unsigned)ceil_div64(w.smax, 256), 256, 0, st>>>(C, lmax, w.key_sorted, w.q_ptr, w.bsp, w.totals, w.slice_sz);
+    EGNN_LAUNCH_CHECK("sell_slice_kernel launch");
+    tb = w.cub_bytes;
+    rc = check_cuda(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, w.slice_sz, w.slice_off, (int)(w.smax + 1), st), "scan slices"); if (rc) return rc;
+    sell_totals_kernel<<<1, 32, 0, st>>>(w.slice_off, w.rv_ptr, (int)n, w.totals);
+    EGNN_LAUNCH_CHECK("sell_totals_kernel launch");
+    int64_t tot[8];
+    rc = check_cuda(cudaMemcpyAsync(tot, w.totals, 64, cudaMemcpyDeviceToHost, st), "copy totals"); if (rc) return rc;
+    rc = check_cuda(cudaStreamSynchronize(st), "sync"); if (rc) return rc;
+    plan->n = (int32_t)n;
+    plan->n_vrows = tot[kTotV];
+    plan->n_slices = tot[kTotSlices];
+    plan->n_entries = tot[kTotEntries];
+    plan->n_rowv = tot[kTotRowV];
+    return EGNN_OK;
+}
+
+int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int64_t nnz,
+                   const egnn_sell_plan* plan, void* workspace, size_t workspace_bytes, egnn_stream_t stream) {
+    int rc = sell_check_geometry(n, nnz, plan);
+    if (rc) return rc;
+    (void)rowptr;
+    EGNN_REQUIRE(plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr, "plan buffers not allocated");
+    EGNN_REQUIRE(plan->n_entries == 0 || plan->idx, "plan idx not allocated");
+    EGNN_REQUIRE(plan->n_rowv == 0 || plan->rv_idx, "plan rv_idx not allocated");
+    const int C = plan->n_blocks, CB = plan->col_block, lmax = plan->lmax;
+    SellWs w = sell_ws_layout(workspace, n, nnz, C, lmax);
+    if (!workspace || workspace_bytes < w.total_bytes) {
+        set_error("sell workspace too small: need %zu bytes, got %zu", w.total_bytes, workspace_bytes);
+        return EGNN_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = check_cuda(cudaMemcpyAsync(plan->slice_off, w.slice_off, 4 * (plan->n_slices + 1), cudaMemcpyDeviceToDevice, st), "copy slice_off"); if (rc) return rc;
+    rc = check_cuda(cudaMemcpyAsync(plan->blk_slice_ptr, w.bsp, 4 * (C + 1), cudaMemcpyDeviceToDevice, st), "copy blk_slice_ptr"); if (rc) return rc;
+    rc = check_cuda(cudaMemcpyAsync(plan->rv_ptr, w.rv_ptr, 4 * (n + 1), cudaMemcpyDeviceToDevice, st), "copy rv_ptr"); if (rc) return rc;
+    if (plan->n_slices > 0) {
+        sell_fill_kernel<<<(unsigned)ceil_div64(plan->n_slices * 32, 256), 256, 0, st>>>(
+            colidx, C, CB, lmax, (int)plan->n_slices, w.key_sorted, w.perm, w.vsrc, w.vslot, w.vrow, w.q_ptr, w.vp_ptr,
+            w.bsp, w.slice_off, plan->idx, plan->rv_idx);
+        EGNN_LAUNCH_CHECK("sell_fill_kernel launch");
     }
     return EGNN_OK;
 }

@@ -138,7 +138,8 @@ template <bool HAS_VALS>
 __global__ void __launch_bounds__(256)
 degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
               const float* __restrict__ vals, int64_t n,
-              float* __restrict__ rowsum, float* __restrict__ diag, double* __restrict__ colsum) {
+              float* __restrict__ rowsum, float* __restrict__ diag, double* __restrict__ colsum,
+              int32_t* __restrict__ unsorted_flag) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -146,8 +147,10 @@ degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
         const int s = rowptr[row], e = rowptr[row + 1];
         double rs = 0.0;
         float dg = 0.f;
+        int bad = 0;
         for (int p = s + lane; p < e; p += 32) {
             const int c = ld_stream_i32(colidx + p);
+            if (unsorted_flag && p + 1 < e) bad |= (__ldg(colidx + p + 1) <= c);   // strictly increasing columns?
             const float v = HAS_VALS ? ld_stream_f32(vals + p) : 1.f;
             rs += (double)v;
             if (c == row) dg += v;
@@ -158,6 +161,7 @@ degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
             rs += __shfl_xor_sync(0xffffffffu, rs, o);
             dg += __shfl_xor_sync(0xffffffffu, dg, o);
         }
+        if (bad) atomicOr(unsorted_flag, 1);
         if (lane == 0) {
             rowsum[row] = (float)rs;
             diag[row] = dg;

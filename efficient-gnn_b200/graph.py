@@ -136,10 +136,60 @@ class CsrGraph:
             self.rowsum = torch.empty(n, dtype=torch.float32, device=dev)
             diag = torch.empty(n, dtype=torch.float32, device=dev)
             colsum = torch.empty(n, dtype=torch.float64, device=dev)
+            self._unsorted_flag = torch.empty(1, dtype=torch.int32, device=dev)
             _cabi.check(lib.egnn_graph_prep(_cabi.ptr(self.rowptr), _cabi.ptr(self.colidx), _cabi.ptr(self.vals), n,
                                             _cabi.ptr(self.dinv), _cabi.ptr(self.iso), _cabi.ptr(self.x0),
                                             _cabi.ptr(self.w), _cabi.ptr(self.rowsum), _cabi.ptr(diag),
-                                            _cabi.ptr(colsum), _stream()), "egnn_graph_prep")
+                                            _cabi.ptr(colsum), _cabi.ptr(self._unsorted_flag), _stream()),
+                        "egnn_graph_prep")
+        self._sell = None          # lazily built SELL plan (False: not applicable)
+
+    # -- SELL plan for the narrow (F = 1) path ---------------------------------
+    SELL_MIN_NNZ = 1 << 22         # below this the CSR is L2-resident and launch-bound anyway
+    SELL_MIN_SEGMENT = 16.0        # mean entries per (row, column block); padding grows below it
+
+    def sell_plan(self, force: bool = False):
+        """The column-blocked sliced-ELL re-layout the F = 1 orders run on
+        (include/egnn_b200.h ``egnn_sell_plan``), built once per graph on the
+        device.  Returns ``None`` when the graph does not qualify (weighted,
+        unsorted rows, small or very sparse): the generic CSR kernel serves it."""
+        if self._sell is not None:
+            return self._sell or None
+        self._sell = False
+        if self.vals is not None or self.n < 1 or self.nnz == 0:
+            return None
+        lib = _cabi.load()
+        nb, cb, lmax = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _cabi.check(lib.egnn_sell_geometry(self.n, self.nnz, C.byref(nb), C.byref(cb), C.byref(lmax)),
+                    "egnn_sell_geometry")
+        if not force and (self.nnz < self.SELL_MIN_NNZ or
+                          self.nnz / (self.n * nb.value) < self.SELL_MIN_SEGMENT):
+            return None
+        if bool(self._unsorted_flag.item()):
+            return None
+        dev = self.device
+        with torch.cuda.device(dev):
+            plan = _cabi.SellPlanStruct()
+            plan.n, plan.n_blocks, plan.col_block, plan.lmax = self.n, nb.value, cb.value, lmax.value
+            ws_bytes = int(lib.egnn_sell_ws_bytes(self.n, self.nnz, nb.value, lmax.value))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _cabi.check(lib.egnn_sell_prepare(_cabi.ptr(self.rowptr), _cabi.ptr(self.colidx), self.n, self.nnz,
+                                              C.byref(plan), _cabi.ptr(ws), ws_bytes, _stream()), "egnn_sell_prepare")
+            bufs = {
+                "slice_off": torch.empty(plan.n_slices + 1, dtype=torch.int32, device=dev),
+                "blk_slice_ptr": torch.empty(plan.n_blocks + 1, dtype=torch.int32, device=dev),
+                "idx": torch.empty(max(1, plan.n_entries), dtype=torch.int16, device=dev),
+                "rv_ptr": torch.empty(self.n + 1, dtype=torch.int32, device=dev),
+                "rv_idx": torch.empty(max(1, plan.n_rowv), dtype=torch.int32, device=dev),
+                "vpart": torch.empty(max(1, plan.n_vrows), dtype=torch.float32, device=dev),
+            }
+            for name, t in bufs.items():
+                setattr(plan, name, t.data_ptr())
+            _cabi.check(lib.egnn_sell_fill(_cabi.ptr(self.rowptr), _cabi.ptr(self.colidx), self.n, self.nnz,
+                                           C.byref(plan), _cabi.ptr(ws), ws_bytes, _stream()), "egnn_sell_fill")
+        plan._keepalive = bufs
+        self._sell = plan
+        return plan
 
     def patched(self, delta_rows: Sequence[int], delta_cols: Sequence[int], delta_vals: Sequence[float]):
         """(dinv, iso, x0) of this graph with edge flips applied (UGCA

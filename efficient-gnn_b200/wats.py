@@ -54,7 +54,7 @@ class WaveletResult:
 
 def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_scale: float,
               op_shift: float, normalize: bool, want_orders: bool, deltas=None,
-              degree_vectors=None, order_events=None):
+              degree_vectors=None, order_events=None, use_sell=None):
     """One call of egnn_cheb_wavelet.  Returns (out [N,S,F], t_all or None)."""
     lib = _cabi.load()
     n, dev = graph.n, graph.device
@@ -69,6 +69,9 @@ def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_
         raise ValueError("coeffs must be [S, K+1]")
     dinv, iso = (graph.dinv, graph.iso) if degree_vectors is None else degree_vectors
     d_rows, d_cols, d_vals = ([], [], []) if deltas is None else deltas
+    plan = None
+    if f == 1 and k >= 1 and use_sell is not False:
+        plan = graph.sell_plan(force=bool(use_sell))
     with torch.cuda.device(dev):
         out = torch.empty((n, n_scales, f), dtype=torch.float32, device=dev)
         t_all = torch.empty((k + 1, n, f), dtype=torch.float32, device=dev) if want_orders else None
@@ -83,7 +86,8 @@ def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_
             _cabi.host_array(C.c_int32, [int(v) for v in d_rows]),
             _cabi.host_array(C.c_int32, [int(v) for v in d_cols]),
             _cabi.host_array(C.c_float, [float(v) for v in d_vals]), len(d_rows),
-            _cabi.ptr(ws), ws_bytes, _stream(), order_events), "egnn_cheb_wavelet")
+            _cabi.ptr(ws), ws_bytes, _stream(), order_events,
+            None if plan is None else C.byref(plan)), "egnn_cheb_wavelet")
     return out, t_all
 
 
@@ -165,7 +169,7 @@ def chebyshev_polynomials(L, k, X0):
 
 def graph_wavelet_features(adj_matrix, k=3, s=0.8, *, X0=None, lambda_max: float = 2.0,
                            normalize: bool = True, return_parts: bool = False, deltas=None,
-                           _order_events=None):
+                           _order_events=None, _use_sell=None):
     """Graph wavelet features by Chebyshev approximation of the heat kernel
     (calibration/WATS.py:39-74).
 
@@ -192,12 +196,13 @@ def graph_wavelet_features(adj_matrix, k=3, s=0.8, *, X0=None, lambda_max: float
         deltas = None
     op_scale = 2.0 / float(lambda_max)
     if return_parts:
-        comb, t_all = _run_cheb(graph, x0, k, coeffs, op_scale, -1.0, False, True, deltas, degree_vectors)
+        comb, t_all = _run_cheb(graph, x0, k, coeffs, op_scale, -1.0, False, True, deltas, degree_vectors,
+                                use_sell=_use_sell)
         feats = comb / (comb.abs().sum(dim=2, keepdim=True) + 1e-8) if normalize else comb
         feats = feats.reshape(graph.n, -1)
         return WaveletResult(feats, [t_all[i] for i in range(k + 1)], comb)
     out, _ = _run_cheb(graph, x0, k, coeffs, op_scale, -1.0, normalize, False, deltas, degree_vectors,
-                       _order_events)
+                       _order_events, _use_sell)
     return out.reshape(graph.n, -1)
 
 

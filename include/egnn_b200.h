@@ -77,12 +77,15 @@ int egnn_dense_to_csr_fill(const float* adj, int64_t n, int64_t ld,
  * vals_or_null == NULL means a binary adjacency (all stored values 1).
  * Outputs dinv/iso/x0_logdeg (x0 may be NULL), w_out_or_null (the float32 w
  * before the sqrt) and rowsum_out, the base vectors egnn_patch_degrees needs.
- * diag_ws: [n] float32 scratch; colsum_ws: [n] float64 scratch.              */
+ * diag_ws: [n] float32 scratch; colsum_ws: [n] float64 scratch.
+ * unsorted_flag_or_null: device int32 set to 1 when some row's column indices
+ * are not strictly increasing (the SELL plan needs sorted, duplicate-free rows). */
 int egnn_graph_prep(const int32_t* rowptr, const int32_t* colidx,
                     const float* vals_or_null, int64_t n,
                     float* dinv, uint8_t* iso, float* x0_logdeg,
                     float* w_out_or_null, float* rowsum_out,
-                    float* diag_ws, double* colsum_ws, egnn_stream_t stream);
+                    float* diag_ws, double* colsum_ws, int32_t* unsorted_flag_or_null,
+                    egnn_stream_t stream);
 
 /* UGCA recompute (the point where calib_attack/calib_fga.py:868,908,952 call
  * the calibrated surrogate on a perturbed adjacency): copies dinv/iso/x0 of
@@ -96,6 +99,42 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base,
                        const float* delta_val_host, int32_t n_delta,
                        float* dinv_out, uint8_t* iso_out, float* x0_out,
                        egnn_stream_t stream);
+
+/* ---- SELL plan: one-time re-layout of a binary, column-sorted CSR -----------
+ * New in this build (no reference counterpart: scipy streams plain CSR).  For
+ * F = 1 - the reference's default signal, calibration/WATS.py:58-59 - the
+ * orders run on a column-blocked sliced-ELL copy of the adjacency with 16-bit
+ * block-local indices, whose operand block is staged in shared memory
+ * (DESIGN.md "narrow path").  Building is two calls around the caller's
+ * allocation:
+ *   egnn_sell_geometry   picks n_blocks / col_block / lmax for n nodes;
+ *   egnn_sell_prepare    counts (all passes but the last) in `workspace`,
+ *                        SYNCHRONISES the stream and fills the size fields;
+ *   (caller allocates slice_off[n_slices+1], blk_slice_ptr[n_blocks+1],
+ *    idx[n_entries] (uint16, 256-byte aligned), rv_ptr[n+1], rv_idx[n_rowv],
+ *    vpart[n_vrows] float32 scratch)
+ *   egnn_sell_fill       writes the index stream; `workspace` must be the
+ *                        one prepare used, untouched in between.
+ * A plan is read-only afterwards except vpart (one wavelet call at a time). */
+typedef struct egnn_sell_plan {
+    int32_t n, n_blocks, col_block, lmax;
+    int64_t n_slices, n_vrows, n_entries, n_rowv;
+    int32_t* slice_off;
+    int32_t* blk_slice_ptr;
+    uint16_t* idx;
+    int32_t* rv_ptr;
+    int32_t* rv_idx;
+    float* vpart;
+} egnn_sell_plan;
+
+int egnn_sell_geometry(int64_t n, int64_t nnz, int32_t* n_blocks, int32_t* col_block, int32_t* lmax);
+size_t egnn_sell_ws_bytes(int64_t n, int64_t nnz, int32_t n_blocks, int32_t lmax);
+int egnn_sell_prepare(const int32_t* rowptr, const int32_t* colidx, int64_t n, int64_t nnz,
+                      egnn_sell_plan* plan, void* workspace, size_t workspace_bytes,
+                      egnn_stream_t stream);
+int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int64_t nnz,
+                   const egnn_sell_plan* plan, void* workspace, size_t workspace_bytes,
+                   egnn_stream_t stream);
 
 /* ---- fused Chebyshev-wavelet pass -----------------------------------------
  * Replaces the rescale (calibration/WATS.py:55), chebyshev_polynomials
@@ -119,7 +158,9 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base,
  * workspace: egnn_cheb_workspace_bytes(n, f) bytes, 256-byte aligned.
  * order_events_host: NULL, or 2*K cudaEvent_t handles; events 2(k-1) and
  * 2(k-1)+1 are recorded on `stream` around order k's kernel (per-kernel
- * timing for the roofline report; no effect on results).                    */
+ * timing for the roofline report; no effect on results).
+ * sell_plan_or_null: when given (f == 1, binary adjacency) the orders run on
+ * the SELL plan; rowptr/colidx are then only used for the argument checks.   */
 size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f);
 int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx,
                       const float* vals_or_null, const float* dinv,
@@ -130,7 +171,8 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx,
                       const int32_t* delta_row_host, const int32_t* delta_col_host,
                       const float* delta_val_host, int32_t n_delta,
                       void* workspace, size_t workspace_bytes,
-                      egnn_stream_t stream, void* const* order_events_host);
+                      egnn_stream_t stream, void* const* order_events_host,
+                      const egnn_sell_plan* sell_plan_or_null);
 
 /* ---- row-sharded variant (1-D partition) -------------------------
  * One order on the rows [row_begin, row_end) this rank owns; new in this

@@ -34,8 +34,14 @@ def rel_max_err(got, ref):
 
 
 def elementwise_ok(got, ref, tol=1e-5):
-    """abs(delta) <= tol * max(|ref|, 1e-3 * ||ref||_inf) for every element."""
+    """abs(delta) <= tol * max(|ref|, 1e-2 * ||ref||_inf) for every element.
+
+    SURVEY 8c proposed a floor of 1e-3 * ||ref||_inf, i.e. an absolute error of
+    1e-8 * ||ref||_inf - below float32 resolution (eps = 6e-8) wherever a row
+    sum cancels, so no float32 implementation can meet it; 1e-2 keeps the
+    bound at ~1.7 eps * ||ref||_inf.  The norm-wise 1e-5 bound (north_star) is
+    checked separately and is met with ~100x margin."""
     ref = np.asarray(ref, dtype=np.float64)
     got = np.asarray(got, dtype=np.float64)
-    floor = 1e-3 * np.abs(ref).max()
+    floor = 1e-2 * np.abs(ref).max()
     return bool(np.all(np.abs(got - ref) <= tol * np.maximum(np.abs(ref), floor) + 1e-30))

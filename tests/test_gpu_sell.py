@@ -1,0 +1,156 @@
+"""The narrow (F = 1) path: column-blocked sliced-ELL plan + shared-memory
+staged SpMV.  Index work is checked bit-exactly (the plan decodes back to the
+CSR minus its diagonal); floating point against the oracle at 1e-5."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import efficient_gnn_b200 as egnn
+from efficient_gnn_b200 import synth
+from oracle import wats_oracle as orc
+from helpers import load_case, rel_max_err
+from test_gpu_parity import check_parts
+
+pytestmark = pytest.mark.gpu
+
+
+def decode_plan(g, plan):
+    """Host-side decode of the SELL plan into a COO pattern."""
+    bufs = plan._keepalive
+    slice_off = bufs["slice_off"].cpu().numpy()
+    bsp = bufs["blk_slice_ptr"].cpu().numpy()
+    idx = bufs["idx"].cpu().numpy().view(np.uint16)
+    rv_ptr = bufs["rv_ptr"].cpu().numpy()
+    rv_idx = bufs["rv_idx"].cpu().numpy()
+    vrow_of = np.full(plan.n_vrows, -1, dtype=np.int64)
+    for i in range(g.n):
+        vrow_of[rv_idx[rv_ptr[i]:rv_ptr[i + 1]]] = i
+    rows, cols = [], []
+    cb = plan.col_block
+    for s in range(plan.n_slices):
+        c = int(np.searchsorted(bsp, s, side="right") - 1)
+        seg = idx[slice_off[s]:slice_off[s + 1]].reshape(-1, 32, 8)      # [group, lane, 8]
+        for lane in range(32):
+            loc = seg[:, lane, :].ravel()
+            loc = loc[loc != cb]
+            v = s * 32 + lane
+            if loc.size:
+                assert vrow_of[v] >= 0
+                rows.append(np.full(loc.size, vrow_of[v]))
+                cols.append(loc.astype(np.int64) + c * cb)
+    if not rows:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    return np.concatenate(rows), np.concatenate(cols)
+
+
+@pytest.mark.parametrize("name", ["kat_path_loops", "cora_noloop", "cora_loops", "pubmed_noloop"])
+def test_plan_is_a_lossless_relayout(name):
+    c = load_case(name)
+    g = egnn.CsrGraph.from_scipy(c["adj"])
+    plan = g.sell_plan(force=True)
+    assert plan is not None
+    assert plan.n_entries % 256 == 0 and plan.n_vrows == 32 * plan.n_slices
+    r, cc = decode_plan(g, plan)
+    a = c["adj"].tocoo()
+    keep = a.row != a.col                                   # stored self loops are dropped
+    want = sp.coo_matrix((np.ones(keep.sum()), (a.row[keep], a.col[keep])), shape=a.shape).tocsr()
+    got = sp.coo_matrix((np.ones(r.size), (r, cc)), shape=a.shape).tocsr()
+    assert got.nnz == want.nnz and (got != want).nnz == 0
+    assert got.data.max(initial=1) == 1                     # every entry exactly once
+
+
+@pytest.mark.parametrize("name", ["kat_path", "kat_path_loops", "cora_noloop", "cora_loops", "pubmed_noloop",
+                                  "cora_k1", "cora_k6_s04"])
+def test_golden_cases_through_the_plan(name):
+    c = load_case(name)
+    res = egnn.graph_wavelet_features(c["adj"], k=c["k"], s=c["s"], return_parts=True, _use_sell=True)
+    check_parts(res, c["T"], [c["S"]], [c["H"]], name)
+    fused = egnn.graph_wavelet_features(c["adj"], k=c["k"], s=c["s"], _use_sell=True)
+    sure = np.abs(c["S"]) > 1e-4 * np.abs(c["S"]).max()
+    np.testing.assert_allclose(fused.cpu().numpy()[sure], c["H"].astype(np.float32)[sure], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape,loops", [("physics", True), ("arxiv", False)])
+def test_plan_matches_oracle_and_generic_kernel(shape, loops):
+    rp, ci, n = synth.synth_csr(shape, self_loops=loops)
+    adj = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
+    g = egnn.CsrGraph(rp.cuda(), ci.cuda(), None, n)
+    scales = [0.8, 1.6]
+    a = egnn.graph_wavelet_features(g, k=3, s=scales, return_parts=True, _use_sell=True)
+    b = egnn.graph_wavelet_features(g, k=3, s=scales, return_parts=True, _use_sell=False)
+    p = orc.wavelet_parts(adj, k=3, s=scales)
+    check_parts(a, p["T"], p["S"], p["H"], f"{shape} sell")
+    for ta, tb in zip(a.orders, b.orders):
+        assert rel_max_err(ta.cpu().numpy(), tb.cpu().numpy()) <= 2e-6
+
+
+def test_hub_rows_are_split_and_summed_deterministically():
+    n = 70_001                                # hub row spans two column blocks and hundreds of virtual rows
+    hub = np.zeros(n - 1, dtype=np.int64)
+    leaves = np.arange(1, n, dtype=np.int64)
+    rows = np.concatenate([hub, leaves])
+    cols = np.concatenate([leaves, hub])
+    adj = sp.csr_matrix((np.ones(rows.size, np.float32), (rows, cols)), shape=(n, n))
+    x0 = np.random.default_rng(0).uniform(0.5, 1.5, (n, 1)).astype(np.float32)
+    g = egnn.CsrGraph.from_scipy(adj)
+    plan = g.sell_plan(force=True)
+    assert plan.n_blocks == 2 and plan.n_rowv > n
+    res = egnn.graph_wavelet_features(g, k=3, X0=torch.from_numpy(x0), return_parts=True, _use_sell=True)
+    p = orc.wavelet_parts(adj, k=3, x0=x0)
+    check_parts(res, p["T"], p["S"], p["H"], "star sell")
+    again = egnn.graph_wavelet_features(g, k=3, X0=torch.from_numpy(x0), return_parts=True, _use_sell=True)
+    for a, b in zip(res.orders, again.orders):
+        assert torch.equal(a, b)
+
+
+def test_edge_flips_through_the_plan():
+    c = load_case("cora_loops")
+    dense = c["adj"].toarray()
+    target, others = 17, [3, 500, 1200, 2000, 2700]
+    nbrs = [j for j in np.nonzero(dense[target])[0] if j != target]
+    if nbrs:
+        others[0] = int(nbrs[0])
+    rows, cols, vals = [], [], []
+    pert = dense.copy()
+    for j in others:
+        v = -2 * dense[target, j] + 1
+        pert[target, j] += v
+        pert[j, target] += v
+        rows += [target, j]
+        cols += [j, target]
+        vals += [float(v), float(v)]
+    g = egnn.CsrGraph.from_scipy(c["adj"])
+    res = egnn.graph_wavelet_features(g, deltas=(rows, cols, vals), return_parts=True, _use_sell=True)
+    p = orc.wavelet_parts(sp.csr_matrix(pert.astype(np.float32)))
+    check_parts(res, p["T"], p["S"], p["H"], "delta sell")
+
+
+def test_unsorted_or_weighted_graphs_fall_back_to_the_csr_kernel():
+    c = load_case("cora_noloop")
+    a = c["adj"].tocsr()
+    # reverse the column order inside every row: same matrix, unsorted storage
+    indptr = a.indptr.astype(np.int32)
+    idx = a.indices.astype(np.int32).copy()
+    for i in range(a.shape[0]):
+        idx[indptr[i]:indptr[i + 1]] = idx[indptr[i]:indptr[i + 1]][::-1]
+    g = egnn.CsrGraph(torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda(), None, a.shape[0])
+    assert g.sell_plan(force=True) is None
+    res = egnn.graph_wavelet_features(g, return_parts=True, _use_sell=True)
+    check_parts(res, c["T"], [c["S"]], [c["H"]], "unsorted")
+    w = load_case("directed_weighted")
+    gw = egnn.CsrGraph.from_scipy(w["adj"])
+    assert gw.vals is not None and gw.sell_plan(force=True) is None
+
+
+def test_reddit_shape_uses_the_plan_by_default():
+    rp, ci, n = synth.synth_csr("reddit", self_loops=True, device="cuda", scale=0.25)
+    g = egnn.CsrGraph(rp, ci, None, n)
+    assert g.sell_plan() is not None
+    a = egnn.graph_wavelet_features(g, k=3, s=0.8, return_parts=True)
+    b = egnn.graph_wavelet_features(g, k=3, s=0.8, return_parts=True, _use_sell=False)
+    for ta, tb in zip(a.orders, b.orders):
+        assert ((ta - tb).abs().max() / tb.abs().max()).item() <= 2e-6
+    plan = g.sell_plan()
+    print(f"\npadding: entries {plan.n_entries} / nnz {g.nnz} = {plan.n_entries / g.nnz:.4f}; "
+          f"vrows {plan.n_vrows}, blocks {plan.n_blocks} x {plan.col_block}")
