@@ -71,6 +71,68 @@ template <> struct FeatVec<4> {
 
 constexpr int kOrderBlock = 256;
 constexpr int kNzUnroll = 4;
+constexpr int kChunkIters = 16;          // fp32 partial sums cover <= 64 entries, then spill into fp64
+constexpr int kLongRowIters = 8;         // rows needing more loop trips than this go to the whole warp
+
+// One lane's share of a row: entries q_first, q_first + stride, ... < q_end.
+// Two-level summation: float32 FMAs over chunks of kChunkIters * kNzUnroll
+// entries, chunk totals added in float64 (the oracle accumulates in float64;
+// long rows of equal addends would otherwise round the same way every step).
+template <int VEC, int U, bool HAS_VALS, bool PRESCALED>
+__device__ __forceinline__ void accumulate_row(const OrderParams& p, int q_first, int q_end, int stride,
+                                               int grow, const int (&fidx)[U], const bool (&fok)[U],
+                                               float (&acc)[U][VEC]) {
+    const int F = p.F;
+    double hi[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { hi[u][v] = 0.0; acc[u][v] = 0.f; }
+    int q0 = q_first;
+    while (q0 < q_end) {
+        for (int it = 0; it < kChunkIters && q0 < q_end; ++it, q0 += stride * kNzUnroll) {
+            int c[kNzUnroll];
+            float w[kNzUnroll];
+#pragma unroll
+            for (int j = 0; j < kNzUnroll; ++j) {
+                const int q = q0 + j * stride;
+                const bool ok = q < q_end;
+                c[j] = ok ? ld_stream_i32(p.colidx + q) : grow;
+                float wv = 0.f;
+                if (ok) wv = HAS_VALS ? ld_stream_f32(p.vals + q) : 1.f;
+                w[j] = wv;
+            }
+#pragma unroll
+            for (int j = 0; j < kNzUnroll; ++j) {
+                if (c[j] == grow) w[j] = 0.f;                  // stored self loops are not part of L
+                if (!PRESCALED) w[j] *= __ldg(p.dinv + c[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < kNzUnroll; ++j) {
+                const float* src = p.gsrc + (int64_t)c[j] * F;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (fok[u]) {
+                        FeatVec<VEC> x;
+                        x.load(src + fidx[u]);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[u][v] = fmaf(w[j], x.v[v], acc[u][v]);
+                    }
+                }
+            }
+        }
+        if (q0 < q_end) {                                       // more chunks follow: spill
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { hi[u][v] += (double)acc[u][v]; acc[u][v] = 0.f; }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[u][v] = (float)(hi[u][v] + (double)acc[u][v]);
+}
 
 template <int VEC, int U, bool HAS_VALS, bool PRESCALED>
 __global__ void __launch_bounds__(kOrderBlock)
@@ -90,7 +152,7 @@ cheb_order_kernel(const __grid_constant__ OrderParams p) {
     const int64_t warp_global = (int64_t)blockIdx.x * (kOrderBlock / 32) + (threadIdx.x >> 5);
     const int64_t row = warp_global * rows_per_warp + sub;
     const bool row_ok = row < p.n_rows;
-    const int64_t grow = p.row0 + (row_ok ? row : 0);
+    const int grow = (int)(p.row0 + (row_ok ? row : 0));
     const int f_tile = blockIdx.y * (FL * VEC * U);
 
     int fidx[U];
@@ -101,58 +163,46 @@ cheb_order_kernel(const __grid_constant__ OrderParams p) {
         fok[u] = fidx[u] < F;
     }
 
-    float acc[U][VEC];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[u][v] = 0.f;
-
     int start = 0, end = 0;
     if (row_ok) {
         start = __ldg(p.rowptr + row);
         end = __ldg(p.rowptr + row + 1);
     }
 
-    {
-        for (int q0 = start + nzl; q0 < end; q0 += NZ * kNzUnroll) {
-            int c[kNzUnroll];
-            float w[kNzUnroll];
-#pragma unroll
-            for (int j = 0; j < kNzUnroll; ++j) {
-                const int q = q0 + j * NZ;
-                const bool ok = q < end;
-                c[j] = ok ? ld_stream_i32(p.colidx + q) : (int)grow;
-                float wv = 0.f;
-                if (ok) wv = HAS_VALS ? ld_stream_f32(p.vals + q) : 1.f;
-                w[j] = wv;
-            }
-#pragma unroll
-            for (int j = 0; j < kNzUnroll; ++j) {
-                if (c[j] == (int)grow) w[j] = 0.f;            // stored self loops are not part of L
-                if (!PRESCALED) w[j] *= __ldg(p.dinv + c[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < kNzUnroll; ++j) {
-                const float* src = p.gsrc + (int64_t)c[j] * F;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (fok[u]) {
-                        FeatVec<VEC> x;
-                        x.load(src + fidx[u]);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) acc[u][v] = fmaf(w[j], x.v[v], acc[u][v]);
-                    }
-                }
-            }
-        }
-    }
-
-    // combine the NZ partial sums of each (row, feature lane)
+    // rows of ordinary length: the row's lane group walks it; hub rows are
+    // deferred to the whole warp (warp-per-row), so one lane group never
+    // serialises tens of thousands of entries.
+    const bool is_long = (group < 32) && (end - start > NZ * kNzUnroll * kLongRowIters);
+    float acc[U][VEC];
+    accumulate_row<VEC, U, HAS_VALS, PRESCALED>(p, start + nzl, is_long ? start : end, NZ, grow, fidx, fok, acc);
     for (int o = FL; o < group; o <<= 1) {
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[u][v] += __shfl_xor_sync(0xffffffffu, acc[u][v], o);
+    }
+    unsigned long_mask = __ballot_sync(0xffffffffu, is_long && gl == 0);
+    while (long_mask) {
+        const int leader = __ffs(long_mask) - 1;
+        long_mask &= long_mask - 1;
+        const int l_start = __shfl_sync(0xffffffffu, start, leader);
+        const int l_end = __shfl_sync(0xffffffffu, end, leader);
+        const int l_grow = __shfl_sync(0xffffffffu, grow, leader);
+        float part[U][VEC];
+        accumulate_row<VEC, U, HAS_VALS, PRESCALED>(p, l_start + (lane >> p.fl_log2), l_end, 32 >> p.fl_log2,
+                                                    l_grow, fidx, fok, part);
+        for (int o = FL; o < 32; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) part[u][v] += __shfl_xor_sync(0xffffffffu, part[u][v], o);
+        }
+        if (sub == (leader >> glog)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[u][v] = part[u][v];
+        }
     }
 
     const bool writer = row_ok && (nzl == 0);
@@ -160,7 +210,7 @@ cheb_order_kernel(const __grid_constant__ OrderParams p) {
     // edge flips on top of the CSR (UGCA recompute); tiny host-provided list
     if (p.delta.n > 0 && writer) {
         for (int e = 0; e < p.delta.n; ++e) {
-            if (p.delta.row[e] == (int)grow && p.delta.col[e] != (int)grow) {
+            if (p.delta.row[e] == grow && p.delta.col[e] != grow) {
                 const int c = p.delta.col[e];
                 float w = p.delta.val[e];
                 if (!PRESCALED) w *= __ldg(p.dinv + c);

@@ -322,11 +322,15 @@ __global__ void __launch_bounds__(256)
 sell_epilogue_kernel(const __grid_constant__ SellEpilogueParams p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    float acc = 0.f;
+    // a hub row owns hundreds of virtual rows: add their partials in float64,
+    // always in the same order (deterministic)
+    double accd = 0.0;
     const int e = __ldg(p.rv_ptr + i + 1);
-    for (int t = __ldg(p.rv_ptr + i); t < e; ++t) acc += __ldg(p.vpart + __ldg(p.rv_idx + t));
+    for (int t = __ldg(p.rv_ptr + i); t < e; ++t) accd += (double)__ldg(p.vpart + __ldg(p.rv_idx + t));
     for (int d = 0; d < p.delta.n; ++d)
-        if (p.delta.row[d] == i && p.delta.col[d] != i) acc = fmaf(p.delta.val[d], __ldg(p.y_prev + p.delta.col[d]), acc);
+        if (p.delta.row[d] == i && p.delta.col[d] != i)
+            accd += (double)p.delta.val[d] * (double)__ldg(p.y_prev + p.delta.col[d]);
+    const float acc = (float)accd;
     const float di = __ldg(p.dinv + i);
     const float theta = fmaf(p.a, 1.f - (float)__ldg(p.iso + i), p.b);
     float xprev = 0.f;

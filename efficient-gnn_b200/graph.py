@@ -75,9 +75,10 @@ class CsrGraph:
             nnz, nonbinary = int(meta[0]), bool(meta[1])
             colidx = torch.empty(nnz, dtype=torch.int32, device=adj.device)
             vals = torch.empty(nnz, dtype=torch.float32, device=adj.device) if nonbinary else None
-            _cabi.check(lib.egnn_dense_to_csr_fill(_cabi.ptr(adj), n, adj.stride(0), _cabi.ptr(rowptr),
-                                                   _cabi.ptr(colidx), _cabi.ptr(vals), _stream()),
-                        "egnn_dense_to_csr_fill")
+            if nnz > 0:
+                _cabi.check(lib.egnn_dense_to_csr_fill(_cabi.ptr(adj), n, adj.stride(0), _cabi.ptr(rowptr),
+                                                       _cabi.ptr(colidx), _cabi.ptr(vals), _stream()),
+                            "egnn_dense_to_csr_fill")
         return cls(rowptr, colidx, vals, n)
 
     @classmethod

@@ -120,8 +120,9 @@ class LaplacianOperator:
             if sp.issparse(other):
                 if other.shape != (n, n):
                     raise ValueError("shape mismatch")
+                o = other.tocoo()
                 d = other.diagonal()
-                if other.nnz > n or (other - sp.diags(d)).nnz != 0 or not np.all(d == d[0]):
+                if np.any(o.row[o.data != 0] != o.col[o.data != 0]) or not np.all(d == d[0]):
                     raise ValueError("only multiples of the identity can be added to the operator")
                 return float(d[0])
         except ImportError:   # pragma: no cover
