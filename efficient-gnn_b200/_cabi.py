@@ -32,6 +32,10 @@ SYMBOLS = {
     "egnn_cheb_workspace_bytes": (_SZ, [_I64, _I32]),
     "egnn_cheb_wavelet": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, _F32, _F32,
                                     _P, _P, _I32, _P, _P, _P, _I32, _P, _SZ, _P, _P, _P]),
+    "egnn_sell_order_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _F32, _F32,
+                                          _I32, _P]),
+    "egnn_prescale": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P]),
+    "egnn_graph_prep_sharded": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "egnn_cheb_order_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                           _I64, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _P, _F32, _F32,
                                           _I32, _I32, _P]),
@@ -41,6 +45,7 @@ SYMBOLS = {
 class SellPlanStruct(C.Structure):
     """Mirror of ``egnn_sell_plan`` (include/egnn_b200.h)."""
     _fields_ = [("n", C.c_int32), ("n_blocks", C.c_int32), ("col_block", C.c_int32), ("lmax", C.c_int32),
+                ("n_cols", C.c_int32), ("row0", C.c_int32),
                 ("n_slices", C.c_int64), ("n_vrows", C.c_int64), ("n_entries", C.c_int64), ("n_rowv", C.c_int64),
                 ("slice_off", C.c_void_p), ("blk_slice_ptr", C.c_void_p), ("idx", C.c_void_p),
                 ("rv_ptr", C.c_void_p), ("rv_idx", C.c_void_p), ("vpart", C.c_void_p)]

@@ -76,7 +76,7 @@ constexpr int kLongRowIters = 8;         // rows needing more loop trips than th
 
 // One lane's share of a row: entries q_first, q_first + stride, ... < q_end.
 // Two-level summation: float32 FMAs over chunks of kChunkIters * kNzUnroll
-// entries, chunk totals added in float64 (the oracle accumulates in float64;
+// entries, chunk totals added in float64 (the reference (scipy) accumulates in float64;
 // long rows of equal addends would otherwise round the same way every step).
 template <int VEC, int U, bool HAS_VALS, bool PRESCALED>
 __device__ __forceinline__ void accumulate_row(const OrderParams& p, int q_first, int q_end, int stride,

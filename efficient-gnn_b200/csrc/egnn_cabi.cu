@@ -155,10 +155,12 @@ static SellWs sell_ws_layout(void* base, int64_t n, int64_t nnz, int C, int lmax
 
 static int sell_check_geometry(int64_t n, int64_t nnz, const egnn_sell_plan* plan) {
     EGNN_REQUIRE(plan != nullptr, "null plan");
+    EGNN_REQUIRE(plan->n_cols >= 1 && plan->row0 >= 0 && (int64_t)plan->row0 + n <= plan->n_cols,
+                 "row shard [row0, row0 + n) must lie inside n_cols");
     EGNN_REQUIRE(n >= 1 && n < (int64_t(1) << 31) && nnz >= 0 && nnz < (int64_t(1) << 31), "n/nnz out of range");
     EGNN_REQUIRE(plan->n_blocks >= 1 && plan->n_blocks <= kSellMaxBlocks, "n_blocks out of range");
     EGNN_REQUIRE(plan->col_block >= 1 && plan->col_block <= 65535, "col_block must fit 16-bit local indices");
-    EGNN_REQUIRE((int64_t)plan->col_block * plan->n_blocks >= n, "column blocks do not cover n");
+    EGNN_REQUIRE((int64_t)plan->col_block * plan->n_blocks >= plan->n_cols, "column blocks do not cover n_cols");
     EGNN_REQUIRE(plan->lmax >= 8 && plan->lmax <= 65536 && plan->lmax % 8 == 0, "lmax must be a multiple of 8 in [8, 65536]");
     EGNN_REQUIRE((int64_t)plan->n_blocks * n < (int64_t(1) << 30), "n_blocks * n too large");
     return EGNN_OK;
@@ -242,10 +244,10 @@ int egnn_graph_prep(const int32_t* rowptr, const int32_t* colidx, const float* v
     const int g = grid_for(n * 32, 256);
     if (vals_or_null)
         degree_kernel<true><<<g, 256, 0, st>>>(rowptr, colidx, vals_or_null, n, rowsum_out, diag_ws, colsum_ws,
-                                               unsorted_flag_or_null);
+                                               unsorted_flag_or_null, 0);
     else
         degree_kernel<false><<<g, 256, 0, st>>>(rowptr, colidx, nullptr, n, rowsum_out, diag_ws, colsum_ws,
-                                                unsorted_flag_or_null);
+                                                unsorted_flag_or_null, 0);
     EGNN_LAUNCH_CHECK("degree_kernel launch");
     normaliser_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(colsum_ws, diag_ws, rowsum_out, n, dinv, iso,
                                                                    x0_logdeg, w_out_or_null);
@@ -347,12 +349,12 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
 
     if (sell_plan) {
         EGNN_REQUIRE(f == 1 && vals_or_null == nullptr, "the SELL plan serves F = 1 on a binary adjacency");
-        EGNN_REQUIRE(sell_plan->n == n && sell_plan->vpart && sell_plan->slice_off && sell_plan->blk_slice_ptr &&
+        EGNN_REQUIRE(sell_plan->n == n && sell_plan->n_cols == n && sell_plan->row0 == 0 && sell_plan->vpart && sell_plan->slice_off && sell_plan->blk_slice_ptr &&
                      sell_plan->rv_ptr, "SELL plan does not match the graph or is not filled");
         SellEpilogueParams ep{};
         ep.delta = p.delta;
         ep.rv_ptr = sell_plan->rv_ptr; ep.rv_idx = sell_plan->rv_idx; ep.vpart = sell_plan->vpart;
-        ep.dinv = dinv; ep.iso = iso; ep.out = out; ep.n = (int32_t)n; ep.S = n_scales;
+        ep.dinv = dinv; ep.iso = iso; ep.out = out; ep.n = (int32_t)n; ep.S = n_scales; ep.row0 = 0;
         ep.a = op_scale; ep.b = op_shift;
         const size_t smem = sizeof(float) * ((size_t)sell_plan->col_block + 1);
         rc = check_cuda(cudaFuncSetAttribute(sell_spmv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -595,9 +597,97 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
     if (plan->n_slices > 0) {
         sell_fill_kernel<<<(unsigned)ceil_div64(plan->n_slices * 32, 256), 256, 0, st>>>(
             colidx, C, CB, lmax, (int)plan->n_slices, w.key_sorted, w.perm, w.vsrc, w.vslot, w.vrow, w.q_ptr, w.vp_ptr,
-            w.bsp, w.slice_off, plan->idx, plan->rv_idx);
+            w.bsp, w.slice_off, plan->idx, plan->rv_idx, plan->row0);
         EGNN_LAUNCH_CHECK("sell_fill_kernel launch");
     }
+    return EGNN_OK;
+}
+
+int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full, const float* dinv_full,
+                            const uint8_t* iso_full, const float* t_prev_local, const float* t_prev2_local,
+                            float* t_out_local, float* y_out_local, float* out_local, int32_t order,
+                            int32_t k_max, int32_t n_scales, const float* coeffs_host, float op_scale,
+                            float op_shift, int32_t normalize_l1, egnn_stream_t stream) {
+    EGNN_REQUIRE(plan && y_prev_full && dinv_full && iso_full && t_prev_local && out_local && coeffs_host, "null pointer");
+    EGNN_REQUIRE(plan->vpart && plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr, "SELL plan is not filled");
+    EGNN_REQUIRE(order >= 1 && order <= k_max && k_max <= EGNN_MAX_ORDER, "bad order");
+    EGNN_REQUIRE(n_scales >= 1 && n_scales <= EGNN_MAX_SCALES, "n_scales out of range");
+    EGNN_REQUIRE(order == 1 || t_prev2_local, "T_{k-2} missing");
+    if (plan->n == 0) return EGNN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sizeof(float) * ((size_t)plan->col_block + 1);
+    int rc = check_cuda(cudaFuncSetAttribute(sell_spmv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        "cudaFuncSetAttribute(sell_spmv_kernel)");
+    if (rc) return rc;
+    if (plan->n_slices > 0) {
+        sell_spmv_kernel<4><<<device_sm_count(), kSellThreads, smem, st>>>(
+            plan->idx, plan->slice_off, plan->blk_slice_ptr, plan->n_blocks, plan->col_block, (int)plan->n_slices,
+            y_prev_full, plan->n_cols, plan->vpart);
+        EGNN_LAUNCH_CHECK("sell_spmv_kernel launch");
+    }
+    SellEpilogueParams ep{};
+    ep.delta.n = 0;
+    ep.rv_ptr = plan->rv_ptr; ep.rv_idx = plan->rv_idx; ep.vpart = plan->vpart; ep.y_prev = y_prev_full;
+    ep.dinv = dinv_full; ep.iso = iso_full; ep.tprev = t_prev_local; ep.tprev2 = t_prev2_local;
+    ep.tk = t_out_local; ep.y_out = y_out_local; ep.out = out_local;
+    ep.n = plan->n; ep.S = n_scales; ep.first = order == 1; ep.normalize = (order == k_max) && normalize_l1;
+    ep.row0 = plan->row0; ep.a = op_scale; ep.b = op_shift;
+    for (int s = 0; s < n_scales; ++s) {
+        ep.c_prev[s] = coeffs_host[s * (k_max + 1) + order - 1];
+        ep.c_k[s] = coeffs_host[s * (k_max + 1) + order];
+    }
+    sell_epilogue_kernel<<<(unsigned)ceil_div64(plan->n, 256), 256, 0, st>>>(ep);
+    EGNN_LAUNCH_CHECK("sell_epilogue_kernel launch");
+    return EGNN_OK;
+}
+
+int egnn_graph_prep_sharded(const int32_t* rowptr_local, const int32_t* colidx_local, const float* vals_or_null,
+                            int64_t n_global, int64_t row_begin, int64_t n_rows, int32_t phase,
+                            double* colsum_full, float* diag_full, float* rowsum_local, float* dinv_full,
+                            uint8_t* iso_full, float* x0_local, int32_t* unsorted_flag_or_null,
+                            egnn_stream_t stream) {
+    EGNN_REQUIRE(colsum_full && diag_full && rowsum_local, "null pointer");
+    EGNN_REQUIRE(n_global >= 0 && row_begin >= 0 && n_rows >= 0 && row_begin + n_rows <= n_global, "bad row range");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (phase == 0) {      // local rows: row sums, diagonal, partial in-degree (caller all-reduces colsum/diag)
+        EGNN_REQUIRE(rowptr_local != nullptr, "null rowptr");
+        rc = check_cuda(cudaMemsetAsync(colsum_full, 0, sizeof(double) * n_global, st), "memset colsum"); if (rc) return rc;
+        rc = check_cuda(cudaMemsetAsync(diag_full, 0, sizeof(float) * n_global, st), "memset diag"); if (rc) return rc;
+        if (unsorted_flag_or_null) {
+            rc = check_cuda(cudaMemsetAsync(unsorted_flag_or_null, 0, sizeof(int32_t), st), "memset flag"); if (rc) return rc;
+        }
+        if (n_rows == 0) return EGNN_OK;
+        const int g = grid_for(n_rows * 32, 256);
+        if (vals_or_null)
+            degree_kernel<true><<<g, 256, 0, st>>>(rowptr_local, colidx_local, vals_or_null, n_rows, rowsum_local,
+                                                   diag_full + row_begin, colsum_full, unsorted_flag_or_null, row_begin);
+        else
+            degree_kernel<false><<<g, 256, 0, st>>>(rowptr_local, colidx_local, nullptr, n_rows, rowsum_local,
+                                                    diag_full + row_begin, colsum_full, unsorted_flag_or_null, row_begin);
+        EGNN_LAUNCH_CHECK("degree_kernel launch");
+        return EGNN_OK;
+    }
+    EGNN_REQUIRE(phase == 1 && dinv_full && iso_full, "bad phase or null outputs");
+    if (n_global > 0) {    // after the all-reduce: normaliser of every node, x0 of the local rows
+        normaliser_kernel<<<(unsigned)ceil_div64(n_global, 256), 256, 0, st>>>(colsum_full, diag_full, nullptr, n_global,
+                                                                            dinv_full, iso_full, nullptr, nullptr);
+        EGNN_LAUNCH_CHECK("normaliser_kernel launch");
+    }
+    if (x0_local && n_rows > 0) {
+        logdeg_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, st>>>(rowsum_local, n_rows, x0_local);
+        EGNN_LAUNCH_CHECK("logdeg_kernel launch");
+    }
+    return EGNN_OK;
+}
+
+int egnn_prescale(const float* x, const float* dinv_full, float* y, int64_t n_rows, int32_t f, int64_t row0,
+                  egnn_stream_t stream) {
+    EGNN_REQUIRE(x && dinv_full && y, "null pointer");
+    EGNN_REQUIRE(n_rows >= 0 && f >= 1 && row0 >= 0, "bad shape");
+    if (n_rows == 0) return EGNN_OK;
+    prescale_kernel<<<grid_for(n_rows * f, 256), 256, 0, (cudaStream_t)stream>>>(x, dinv_full, y, n_rows, f, row0);
+    EGNN_LAUNCH_CHECK("prescale_kernel launch");
     return EGNN_OK;
 }
 

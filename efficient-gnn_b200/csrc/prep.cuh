@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256)
 degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
               const float* __restrict__ vals, int64_t n,
               float* __restrict__ rowsum, float* __restrict__ diag, double* __restrict__ colsum,
-              int32_t* __restrict__ unsorted_flag) {
+              int32_t* __restrict__ unsorted_flag, int64_t row0) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -153,7 +153,7 @@ degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
             if (unsorted_flag && p + 1 < e) bad |= (__ldg(colidx + p + 1) <= c);   // strictly increasing columns?
             const float v = HAS_VALS ? ld_stream_f32(vals + p) : 1.f;
             rs += (double)v;
-            if (c == row) dg += v;
+            if (c == row + row0) dg += v;
             atomicAdd(colsum + c, (double)v);
         }
 #pragma unroll
@@ -187,8 +187,14 @@ normaliser_kernel(const double* __restrict__ colsum, const float* __restrict__ d
     normaliser_from_w(w, d, is);
     dinv[i] = d;
     iso[i] = is;
-    if (x0) x0[i] = (float)log1p((double)rowsum[i]);
+    if (x0 && rowsum) x0[i] = (float)log1p((double)rowsum[i]);
     if (w_out) w_out[i] = w;
+}
+
+__global__ void __launch_bounds__(256)
+logdeg_kernel(const float* __restrict__ rowsum, int64_t n, float* __restrict__ x0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x0[i] = (float)log1p((double)rowsum[i]);
 }
 
 struct DeltaList {

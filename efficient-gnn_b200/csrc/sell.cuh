@@ -155,7 +155,7 @@ sell_fill_kernel(const int32_t* __restrict__ colidx, int C, int CB, int lmax, in
                  const int32_t* __restrict__ vrow, const int32_t* __restrict__ q_ptr,
                  const int32_t* __restrict__ vp_ptr, const int32_t* __restrict__ blk_slice_ptr,
                  const int32_t* __restrict__ slice_off, uint16_t* __restrict__ idx,
-                 int32_t* __restrict__ rv_idx) {
+                 int32_t* __restrict__ rv_idx, int row0) {
     const int lane = threadIdx.x & 31;
     const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (s >= n_slices) return;
@@ -169,7 +169,7 @@ sell_fill_kernel(const int32_t* __restrict__ colidx, int C, int CB, int lmax, in
         const int u = perm[q];
         len = lmax - (int)(key_sorted[q] & 0xffffu);
         src = vsrc[u];
-        row = vrow[u];
+        row = vrow[u] + row0;             // global id of the row (diagonal test)
         rv_idx[vslot[u]] = v;
     }
     const int off = slice_off[s];
@@ -311,7 +311,8 @@ struct SellEpilogueParams {
     float* tk;               // or NULL
     float* y_out;            // or NULL
     float* out;              // [n, S]
-    int32_t n, S, first, normalize;
+    int32_t n, S, first, normalize;   // n: rows of this launch
+    int32_t row0;                     // global id of local row 0 (dinv/iso/deltas are global)
     float a, b;
     float c_prev[EGNN_MAX_SCALES];
     float c_k[EGNN_MAX_SCALES];
@@ -328,11 +329,11 @@ sell_epilogue_kernel(const __grid_constant__ SellEpilogueParams p) {
     const int e = __ldg(p.rv_ptr + i + 1);
     for (int t = __ldg(p.rv_ptr + i); t < e; ++t) accd += (double)__ldg(p.vpart + __ldg(p.rv_idx + t));
     for (int d = 0; d < p.delta.n; ++d)
-        if (p.delta.row[d] == i && p.delta.col[d] != i)
+        if (p.delta.row[d] == i + p.row0 && p.delta.col[d] != i + p.row0)
             accd += (double)p.delta.val[d] * (double)__ldg(p.y_prev + p.delta.col[d]);
     const float acc = (float)accd;
-    const float di = __ldg(p.dinv + i);
-    const float theta = fmaf(p.a, 1.f - (float)__ldg(p.iso + i), p.b);
+    const float di = __ldg(p.dinv + p.row0 + i);
+    const float theta = fmaf(p.a, 1.f - (float)__ldg(p.iso + p.row0 + i), p.b);
     float xprev = 0.f;
     if (theta != 0.f || p.first) xprev = p.tprev[i];
     const float lap = fmaf(theta, xprev, -p.a * di * acc);

@@ -172,6 +172,7 @@ class CsrGraph:
         with torch.cuda.device(dev):
             plan = _cabi.SellPlanStruct()
             plan.n, plan.n_blocks, plan.col_block, plan.lmax = self.n, nb.value, cb.value, lmax.value
+            plan.n_cols, plan.row0 = self.n, 0
             ws_bytes = int(lib.egnn_sell_ws_bytes(self.n, self.nnz, nb.value, lmax.value))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             _cabi.check(lib.egnn_sell_prepare(_cabi.ptr(self.rowptr), _cabi.ptr(self.colidx), self.n, self.nnz,

@@ -1,0 +1,443 @@
+"""Row-sharded wavelet features: one process per GPU, 1-D contiguous row
+partition, one exchange of the order's operand per Chebyshev order
+(new in this build - the reference is single-device).
+
+Rank r owns rows ``[r * rows_per, (r + 1) * rows_per)`` of the CSR, of
+``T_k`` and of the output.  Per order k:
+
+* wide signals (generic CSR kernel): the rank's CSR is split once into a
+  local-column and a remote-column half; the local half runs while
+  ``all_gather_into_tensor`` of the ``T_{k-1}`` slabs is in flight on a side
+  stream, the remote half + fused epilogue run when it lands;
+* F = 1 on a binary graph (SELL plan over the rank's rows): the pre-scaled
+  operand ``dinv * T_{k-1}`` (0.93 MB at Reddit size) is gathered, then the
+  shared-memory SpMV + epilogue run on the local rows.
+
+The compute engine is injectable so the host logic (partition, column split,
+exchange order, buffer rotation) is testable on CPU with the gloo backend;
+the product engine is :class:`CudaEngine` (C ABI, no fallback).
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+import json
+import os
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from .wats import heat_coefficients
+
+__all__ = ["RowPartition", "split_columns", "CudaEngine", "DistComm", "ShardedWavelet"]
+
+
+class RowPartition:
+    """Equal contiguous row blocks (the last one may be short)."""
+
+    def __init__(self, n: int, world: int):
+        self.n, self.world = int(n), int(world)
+        self.rows_per = (self.n + self.world - 1) // self.world
+
+    def begin(self, rank: int) -> int:
+        return min(self.n, rank * self.rows_per)
+
+    def end(self, rank: int) -> int:
+        return min(self.n, (rank + 1) * self.rows_per)
+
+    def rows(self, rank: int) -> int:
+        return self.end(rank) - self.begin(rank)
+
+    def slice_csr(self, rowptr: torch.Tensor, colidx: torch.Tensor, rank: int):
+        """The rank's rows of a full CSR (global column ids, rowptr rebased)."""
+        b, e = self.begin(rank), self.end(rank)
+        lo, hi = int(rowptr[b]), int(rowptr[e])
+        return (rowptr[b:e + 1] - rowptr[b]).to(torch.int32).contiguous(), colidx[lo:hi].contiguous()
+
+
+def split_columns(rowptr: torch.Tensor, colidx: torch.Tensor, col_begin: int, col_end: int):
+    """Split a row shard into (local-column CSR, remote-column CSR); entry
+    order inside each row is preserved.  Index plumbing only (torch ops)."""
+    n_rows = rowptr.numel() - 1
+    counts = (rowptr[1:] - rowptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=rowptr.device), counts)
+    is_local = (colidx >= col_begin) & (colidx < col_end)
+    out = []
+    for mask in (is_local, ~is_local):
+        ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=rowptr.device)
+        ptr[1:] = torch.cumsum(torch.bincount(rows[mask], minlength=n_rows), 0)
+        out.append((ptr.to(torch.int32), colidx[mask].contiguous()))
+    return out[0], out[1]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class CudaEngine:
+    """Device side of the sharded path: thin calls into libegnn_b200."""
+
+    SELL_MIN_SEGMENT = 8.0
+
+    def __init__(self, device):
+        _cabi.require_device()
+        self.device = torch.device(device)
+        self.lib = _cabi.load()
+        self.comm_stream = torch.cuda.Stream(device=self.device)
+
+    # -- degree vectors -----------------------------------------------------
+    def prep(self, rowptr, colidx, n_global, row_begin, n_rows, allreduce):
+        dev, lib = self.device, self.lib
+        colsum = torch.empty(n_global, dtype=torch.float64, device=dev)
+        diag = torch.empty(n_global, dtype=torch.float32, device=dev)
+        rowsum = torch.empty(max(1, n_rows), dtype=torch.float32, device=dev)
+        dinv = torch.empty(n_global, dtype=torch.float32, device=dev)
+        iso = torch.empty(n_global, dtype=torch.uint8, device=dev)
+        x0 = torch.empty(max(1, n_rows), dtype=torch.float32, device=dev)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        args = (_cabi.ptr(rowptr), _cabi.ptr(colidx), None, n_global, row_begin, n_rows)
+        _cabi.check(lib.egnn_graph_prep_sharded(*args, 0, _cabi.ptr(colsum), _cabi.ptr(diag), _cabi.ptr(rowsum),
+                                                None, None, None, _cabi.ptr(flag), _stream()), "prep phase 0")
+        allreduce(colsum)
+        allreduce(diag)
+        _cabi.check(lib.egnn_graph_prep_sharded(*args, 1, _cabi.ptr(colsum), _cabi.ptr(diag), _cabi.ptr(rowsum),
+                                                _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(x0), None, _stream()),
+                    "prep phase 1")
+        return dinv, iso, x0[:n_rows], bool(flag.item())
+
+    # -- generic CSR kernel, one order ---------------------------------------
+    def order(self, phase, local, remote, dinv, iso, t_prev_full, t_prev_local, t_prev2_local, t_out_local,
+              out_local, acc_ws, n_global, nnz_hint, row_begin, row_end, f, order, k_max, n_scales, coeffs,
+              op_scale, op_shift, normalize):
+        lp, lc = (None, None) if local is None else local
+        rp, rc = (None, None) if remote is None else remote
+        _cabi.check(self.lib.egnn_cheb_order_sharded(
+            _cabi.ptr(lp), _cabi.ptr(lc), _cabi.ptr(rp), _cabi.ptr(rc), _cabi.ptr(dinv), _cabi.ptr(iso),
+            _cabi.ptr(t_prev_full), _cabi.ptr(t_prev_local), _cabi.ptr(t_prev2_local), _cabi.ptr(t_out_local),
+            _cabi.ptr(out_local), _cabi.ptr(acc_ws), n_global, nnz_hint, row_begin, row_end, f, order, k_max,
+            n_scales, coeffs.ctypes.data_as(C.c_void_p), float(op_scale), float(op_shift), 1 if normalize else 0,
+            phase, _stream()), "egnn_cheb_order_sharded")
+
+    # -- narrow path -----------------------------------------------------------
+    def sell_plan(self, rowptr, colidx, n_rows, n_cols, row0, unsorted):
+        if unsorted or n_rows == 0 or colidx.numel() == 0:
+            return None
+        lib, dev = self.lib, self.device
+        nnz = int(colidx.numel())
+        nb, cb, lmax = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _cabi.check(lib.egnn_sell_geometry(n_cols, nnz, C.byref(nb), C.byref(cb), C.byref(lmax)), "egnn_sell_geometry")
+        if nnz / (n_rows * nb.value) < self.SELL_MIN_SEGMENT:
+            return None
+        plan = _cabi.SellPlanStruct()
+        plan.n, plan.n_blocks, plan.col_block, plan.lmax = n_rows, nb.value, cb.value, lmax.value
+        plan.n_cols, plan.row0 = n_cols, row0
+        ws_bytes = int(lib.egnn_sell_ws_bytes(n_rows, nnz, nb.value, lmax.value))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _cabi.check(lib.egnn_sell_prepare(_cabi.ptr(rowptr), _cabi.ptr(colidx), n_rows, nnz, C.byref(plan),
+                                          _cabi.ptr(ws), ws_bytes, _stream()), "egnn_sell_prepare")
+        bufs = {
+            "slice_off": torch.empty(plan.n_slices + 1, dtype=torch.int32, device=dev),
+            "blk_slice_ptr": torch.empty(plan.n_blocks + 1, dtype=torch.int32, device=dev),
+            "idx": torch.empty(max(1, plan.n_entries), dtype=torch.int16, device=dev),
+            "rv_ptr": torch.empty(n_rows + 1, dtype=torch.int32, device=dev),
+            "rv_idx": torch.empty(max(1, plan.n_rowv), dtype=torch.int32, device=dev),
+            "vpart": torch.empty(max(1, plan.n_vrows), dtype=torch.float32, device=dev),
+        }
+        for name, t in bufs.items():
+            setattr(plan, name, t.data_ptr())
+        _cabi.check(lib.egnn_sell_fill(_cabi.ptr(rowptr), _cabi.ptr(colidx), n_rows, nnz, C.byref(plan),
+                                       _cabi.ptr(ws), ws_bytes, _stream()), "egnn_sell_fill")
+        plan._keepalive = bufs
+        return plan
+
+    def prescale(self, x_local, dinv, y_local, n_rows, f, row0):
+        _cabi.check(self.lib.egnn_prescale(_cabi.ptr(x_local), _cabi.ptr(dinv), _cabi.ptr(y_local), n_rows, f, row0,
+                                           _stream()), "egnn_prescale")
+
+    def sell_order(self, plan, y_full, dinv, iso, t_prev, t_prev2, t_out, y_out, out, order, k_max, n_scales,
+                   coeffs, op_scale, op_shift, normalize):
+        _cabi.check(self.lib.egnn_sell_order_sharded(
+            C.byref(plan), _cabi.ptr(y_full), _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(t_prev), _cabi.ptr(t_prev2),
+            _cabi.ptr(t_out), _cabi.ptr(y_out), _cabi.ptr(out), order, k_max, n_scales,
+            coeffs.ctypes.data_as(C.c_void_p), float(op_scale), float(op_shift), 1 if normalize else 0, _stream()),
+            "egnn_sell_order_sharded")
+
+    # -- stream plumbing ---------------------------------------------------------
+    def side_stream(self):
+        return torch.cuda.stream(self.comm_stream)
+
+    def fork(self):
+        """Side stream waits for everything queued on the compute stream."""
+        self.comm_stream.wait_stream(torch.cuda.current_stream())
+
+    def join(self):
+        """Compute stream waits for the side stream (the exchange)."""
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+
+class DistComm:
+    """Collectives of the path over ``torch.distributed`` (NCCL on GPUs)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def allreduce(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+
+    def allgather(self, full, slab):
+        """``full[rank * rows_per ...] = slab`` of every rank (equal-size slabs)."""
+        if self.world > 1:
+            dist.all_gather_into_tensor(full, slab, group=self.group)
+        else:
+            full.copy_(slab)
+
+
+class ShardedWavelet:
+    """Wavelet features of a row-sharded graph.
+
+    ``rowptr_local`` / ``colidx_local``: the rank's rows (global column ids),
+    rows assigned by :class:`RowPartition`.  ``engine`` defaults to the CUDA
+    engine; tests inject a CPU engine to drive this logic over gloo.
+    """
+
+    def __init__(self, rowptr_local, colidx_local, n_global: int, *, group=None, engine=None, device=None,
+                 use_sell: Optional[bool] = None, comm=None):
+        self.comm = comm if comm is not None else DistComm(group)
+        self.rank, self.world = self.comm.rank, self.comm.world
+        self.n = int(n_global)
+        self.part = RowPartition(self.n, self.world)
+        self.row_begin, self.row_end = self.part.begin(self.rank), self.part.end(self.rank)
+        self.rows = self.row_end - self.row_begin
+        if rowptr_local.numel() != self.rows + 1:
+            raise ValueError(f"rank {self.rank} owns {self.rows} rows but rowptr has {rowptr_local.numel()} entries")
+        self.device = rowptr_local.device if device is None else torch.device(device)
+        self.engine = engine if engine is not None else CudaEngine(self.device)
+        self.rowptr = rowptr_local.to(torch.int32).contiguous()
+        self.colidx = colidx_local.to(torch.int32).contiguous()
+        self.nnz_local = int(self.colidx.numel())
+        self.dinv, self.iso, self.x0, unsorted = self.engine.prep(self.rowptr, self.colidx, self.n, self.row_begin,
+                                                                  self.rows, self._allreduce)
+        self.local_half, self.remote_half = split_columns(self.rowptr, self.colidx, self.row_begin, self.row_end)
+        self.plan = None
+        if use_sell is not False:
+            self.plan = self.engine.sell_plan(self.rowptr, self.colidx, self.rows, self.n, self.row_begin, unsorted)
+        self.launches = 0
+
+    # -- collectives -------------------------------------------------------------
+    def _allreduce(self, t):
+        self.comm.allreduce(t)
+
+    def _allgather(self, full, slab):
+        self.comm.allgather(full, slab)
+
+    # -- the path ------------------------------------------------------------------
+    def features(self, k=3, s=0.8, *, X0_local=None, lambda_max: float = 2.0, normalize: bool = True,
+                 return_parts: bool = False):
+        """Features of the local rows ``[rows, S*F]`` (reference defaults
+        k=3, s=0.8, X0 = log1p(degree)); with ``return_parts`` also the local
+        slabs of every order and the un-normalised combination."""
+        eng, dev = self.engine, self.device
+        k = int(k)
+        coeffs = np.ascontiguousarray(heat_coefficients(k, s), dtype=np.float32)
+        n_scales = coeffs.shape[0]
+        x0 = self.x0.reshape(-1, 1) if X0_local is None else torch.as_tensor(X0_local)
+        if x0.dim() == 1:
+            x0 = x0.reshape(-1, 1)
+        if x0.shape[0] != self.rows:
+            raise ValueError(f"X0_local has {x0.shape[0]} rows, this rank owns {self.rows}")
+        x0 = x0.to(device=dev, dtype=torch.float32).contiguous()
+        f = int(x0.shape[1])
+        rp = self.part.rows_per
+        op_scale, op_shift = 2.0 / float(lambda_max), -1.0
+        fused_norm = normalize and not return_parts
+
+        def slab():
+            return torch.zeros((rp, f), dtype=torch.float32, device=dev)
+
+        out = torch.zeros((max(1, self.rows), n_scales, f), dtype=torch.float32, device=dev)
+        orders = [x0]
+        if k == 0:
+            out[:self.rows] = torch.from_numpy(coeffs[:, 0]).to(dev).reshape(1, -1, 1) * x0.unsqueeze(1)
+        t_prev = slab()
+        t_prev[:self.rows] = x0
+        t_prev2 = None
+        full = torch.empty((self.world * rp, f), dtype=torch.float32, device=dev)
+        use_plan = self.plan is not None and f == 1
+        if use_plan:
+            y_slabs = [slab(), slab()]
+            if self.rows:
+                eng.prescale(t_prev, self.dinv, y_slabs[0], self.rows, f, self.row_begin)
+        else:
+            acc_ws = slab()
+        for order in range(1, k + 1):
+            last = order == k
+            if return_parts:
+                t_out = slab()
+            elif last:
+                t_out = None                  # T_K itself is never read again
+            elif order <= 2:
+                t_out = slab()
+            else:
+                t_out = t_prev2               # in place over T_{k-2} (read-then-write per element)
+            if use_plan:
+                y_prev = y_slabs[(order - 1) & 1]
+                self._allgather(full, y_prev)
+                if self.rows:
+                    eng.sell_order(self.plan, full, self.dinv, self.iso, t_prev, t_prev2, t_out,
+                                   None if last else y_slabs[order & 1], out, order, k, n_scales, coeffs,
+                                   op_scale, op_shift, fused_norm)
+                    self.launches += 2
+            else:
+                # exchange T_{k-1} on the side stream while the local-column half runs
+                eng.fork()
+                with eng.side_stream():
+                    self._allgather(full, t_prev)
+                common = (self.dinv, self.iso)
+                tail = (self.n, max(1, self.nnz_local), self.row_begin, self.row_end, f, order, k, n_scales, coeffs,
+                        op_scale, op_shift, fused_norm)
+                if self.rows:
+                    eng.order(0, self.local_half, None, *common, None, t_prev, t_prev2, t_out, out, acc_ws, *tail)
+                eng.join()
+                if self.rows:
+                    eng.order(1, None, self.remote_half, *common, full, t_prev, t_prev2, t_out, out, acc_ws, *tail)
+                    self.launches += 2
+            if return_parts:
+                orders.append(t_out[:self.rows])
+            t_prev2, t_prev = t_prev, t_out
+        out = out[:self.rows]
+        if k == 0 and fused_norm:
+            out = out / (out.abs().sum(dim=2, keepdim=True) + 1e-8)
+        if return_parts:
+            comb = out
+            feats = comb / (comb.abs().sum(dim=2, keepdim=True) + 1e-8) if normalize else comb
+            return feats.reshape(self.rows, -1), orders, comb
+        return out.reshape(self.rows, -1)
+
+    def gather_features(self, local_feats):
+        """All ranks' feature rows, ``[N, S*F]`` on every rank."""
+        rp = self.part.rows_per
+        pad = torch.zeros((rp, local_feats.shape[1]), dtype=local_feats.dtype, device=local_feats.device)
+        pad[:self.rows] = local_feats
+        full = torch.empty((self.world * rp, local_feats.shape[1]), dtype=local_feats.dtype, device=local_feats.device)
+        self._allgather(full, pad)
+        return full[:self.n]
+
+
+# --------------------------------------------------------------------------- #
+# bench.py entry for N > 1 (launched by torch.distributed.run)                   #
+# --------------------------------------------------------------------------- #
+def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, clock_sampler_cls,
+                physical_gpu_index, scale_list):
+    from . import synth
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    f = args.f or {"reddit": 1, "arxiv": 128, "physics": 1, "pubmed": 1, "cora": 1}[args.workload]
+    k_max, n_scales = args.order, args.scales
+    scales = scale_list(n_scales)
+    sh = synth.SHAPES[args.workload]
+    # every rank generates the same seeded graph in its own HBM and keeps its rows
+    rp_full, ci_full, n = synth.synth_csr(args.workload, self_loops=True, device=dev)
+    nnz = int(ci_full.numel())
+    part = RowPartition(n, world)
+    rp_loc, ci_loc = part.slice_csr(rp_full, ci_full, rank)
+    del rp_full, ci_full
+    torch.cuda.empty_cache()
+    sw = ShardedWavelet(rp_loc, ci_loc, n, device=dev)
+    x0 = None
+    if f > 1:
+        gen = torch.Generator(device=dev).manual_seed(sh.seed)
+        x0 = torch.randn(n, f, device=dev, generator=gen)[sw.row_begin:sw.row_end].contiguous()
+    work = float(nnz) * k_max * f
+
+    def step():
+        return sw.features(k=k_max, s=scales, X0_local=x0)
+
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = clock_sampler_cls(physical_gpu_index(local_rank))
+    sampler.start()
+    sw.launches = 0
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    for _ in range(args.steps):
+        step()
+    stop.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join()
+    ms = torch.tensor([start.elapsed_time(stop) / args.steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    ms_per_step = float(ms.item())
+
+    # end to end: pinned host shard -> device -> features -> host, every step
+    e2e = None
+    if not args.no_e2e:
+        rp_h, ci_h = sw.rowptr.cpu().pin_memory(), sw.colidx.cpu().pin_memory()
+        x0_h = None if x0 is None else x0.cpu().pin_memory()
+        out_h = torch.empty((max(1, sw.rows), n_scales * f), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            g = ShardedWavelet(rp_h.to(dev, non_blocking=True), ci_h.to(dev, non_blocking=True), n, device=dev)
+            xx = None if x0_h is None else x0_h.to(dev, non_blocking=True)
+            feats = g.features(k=k_max, s=scales, X0_local=xx)
+            out_h[:sw.rows].copy_(feats, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / e_steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = torch.tensor([rp_h.numel() * 4 + ci_h.numel() * 4 + (0 if x0_h is None else x0_h.numel() * 4)],
+                           device=dev, dtype=torch.float64)
+        dist.all_reduce(h2d)
+        e2e = {"value": work / float(dt.item()), "unit": unit, "h2d_bytes_per_step": int(h2d.item()),
+               "d2h_bytes_per_step": int(n * n_scales * f * 4), "ms_per_step": float(dt.item()) * 1e3,
+               "steps": e_steps,
+               "entry": "ShardedWavelet(pinned host row shard) + features -> pinned host, per rank"}
+
+    launches = torch.tensor([sw.launches], device=dev, dtype=torch.float64)
+    dist.all_reduce(launches)
+    if rank == 0:
+        b_k = algorithmic_bytes(n, nnz, f, k_max, n_scales)
+        peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+        peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.isfile(peaks) else 6650.0
+        achieved = sum(b_k) / (ms_per_step * 1e-3) / 1e9          # whole step, all ranks: aggregate GB/s
+        line = {
+            "metric": metric, "value": work / (ms_per_step * 1e-3), "unit": unit, "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}-shape", "n": n, "nnz": nnz, "k": k_max, "scales": n_scales,
+                       "f": f, "self_loops": True,
+                       "parallelism": f"{world} row shards, all_gather of the order operand per order (NCCL)",
+                       "path": "sell-f1" if (sw.plan is not None and f == 1) else "csr-split-overlap",
+                       "l2_policy": "per-rank CSR shard %.0f MB; no flush" % (4 * nnz / world / 1e6)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
+                         "frac": achieved / (peak * world), "traffic": None,
+                         "note": "whole step incl. exchange, aggregate over ranks, compulsory-bytes model"},
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()),
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -117,7 +117,8 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base,
  *                        one prepare used, untouched in between.
  * A plan is read-only afterwards except vpart (one wavelet call at a time). */
 typedef struct egnn_sell_plan {
-    int32_t n, n_blocks, col_block, lmax;
+    int32_t n, n_blocks, col_block, lmax; /* n: rows laid out (a row shard or the whole graph) */
+    int32_t n_cols, row0;                 /* columns = global nodes; global id of row 0        */
     int64_t n_slices, n_vrows, n_entries, n_rowv;
     int32_t* slice_off;
     int32_t* blk_slice_ptr;
@@ -127,7 +128,7 @@ typedef struct egnn_sell_plan {
     float* vpart;
 } egnn_sell_plan;
 
-int egnn_sell_geometry(int64_t n, int64_t nnz, int32_t* n_blocks, int32_t* col_block, int32_t* lmax);
+int egnn_sell_geometry(int64_t n_cols, int64_t nnz, int32_t* n_blocks, int32_t* col_block, int32_t* lmax);
 size_t egnn_sell_ws_bytes(int64_t n, int64_t nnz, int32_t n_blocks, int32_t lmax);
 int egnn_sell_prepare(const int32_t* rowptr, const int32_t* colidx, int64_t n, int64_t nnz,
                       egnn_sell_plan* plan, void* workspace, size_t workspace_bytes,
@@ -196,6 +197,38 @@ int egnn_cheb_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
                             int32_t f, int32_t order, int32_t k_max, int32_t n_scales,
                             const float* coeffs_host, float op_scale, float op_shift,
                             int32_t normalize_l1, int32_t phase,
+                            egnn_stream_t stream);
+
+/* One order of the narrow (F = 1) path on a row shard: SELL SpMV over the
+ * rank's plan (plan->n rows starting at plan->row0, plan->n_cols columns)
+ * against the exchanged full operand y_prev_full = dinv (.) T_{k-1} [n_cols],
+ * then the epilogue on the local rows: T_k -> t_out_local (or NULL),
+ * dinv (.) T_k -> y_out_local (the slab the next exchange moves; or NULL),
+ * scale accumulation into out_local [rows, n_scales].                        */
+int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full,
+                            const float* dinv_full, const uint8_t* iso_full,
+                            const float* t_prev_local, const float* t_prev2_local,
+                            float* t_out_local, float* y_out_local, float* out_local,
+                            int32_t order, int32_t k_max, int32_t n_scales,
+                            const float* coeffs_host, float op_scale, float op_shift,
+                            int32_t normalize_l1, egnn_stream_t stream);
+
+/* y[r, :] = dinv_full[row0 + r] * x[r, :]: the gather operand of order 1 on
+ * the narrow path (later orders get it from the epilogue).                   */
+int egnn_prescale(const float* x, const float* dinv_full, float* y, int64_t n_rows,
+                  int32_t f, int64_t row0, egnn_stream_t stream);
+
+/* Degree pass of a row shard (scipy semantics as egnn_graph_prep).  phase 0:
+ * row sums of the local rows, their diagonal entries into diag_full[row_begin..]
+ * and the shard's contribution to the in-degree in colsum_full (both zeroed
+ * first); the caller then sums colsum_full and diag_full over the ranks
+ * (all-reduce).  phase 1: dinv/iso of every node and x0 = log1p(rowsum) of the
+ * local rows.                                                                 */
+int egnn_graph_prep_sharded(const int32_t* rowptr_local, const int32_t* colidx_local,
+                            const float* vals_or_null, int64_t n_global, int64_t row_begin,
+                            int64_t n_rows, int32_t phase, double* colsum_full, float* diag_full,
+                            float* rowsum_local, float* dinv_full, uint8_t* iso_full,
+                            float* x0_local, int32_t* unsorted_flag_or_null,
                             egnn_stream_t stream);
 
 #ifdef __cplusplus

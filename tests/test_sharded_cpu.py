@@ -1,0 +1,158 @@
+"""Host logic of the row-sharded path on CPU: world_size 2 (and 3) over gloo,
+with a NumPy engine standing in for the CUDA kernels.  What is under test is
+the partition, the local/remote column split, the exchange order and the slab
+rotation - the arithmetic here is the oracle's, so any mismatch is plumbing."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class NumpyEngine:
+    """CPU stand-in with the CudaEngine interface (tests only)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def prep(self, rowptr, colidx, n_global, row_begin, n_rows, allreduce):
+        rp, ci = rowptr.numpy(), colidx.numpy()
+        colsum = torch.zeros(n_global, dtype=torch.float64)
+        diag = torch.zeros(n_global, dtype=torch.float32)
+        rows = np.repeat(np.arange(n_rows), np.diff(rp)) + row_begin
+        np.add.at(colsum.numpy(), ci, 1.0)
+        on = rows == ci
+        diag.numpy()[rows[on]] = 1.0
+        rowsum = np.diff(rp).astype(np.float32)
+        allreduce(colsum)
+        allreduce(diag)
+        w = colsum.numpy().astype(np.float32) - diag.numpy()
+        iso = w == 0
+        dinv = np.where(iso, 1.0, 1.0 / np.sqrt(np.where(iso, 1.0, w).astype(np.float64))).astype(np.float32)
+        return (torch.from_numpy(dinv), torch.from_numpy(iso.astype(np.uint8)),
+                torch.from_numpy(np.log1p(rowsum)), False)
+
+    def sell_plan(self, *a, **k):
+        return None
+
+    def fork(self):
+        self.calls.append("fork")
+
+    def join(self):
+        self.calls.append("join")
+
+    def side_stream(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def order(self, phase, local, remote, dinv, iso, t_prev_full, t_prev_local, t_prev2_local, t_out_local,
+              out_local, acc_ws, n_global, nnz_hint, row_begin, row_end, f, order, k_max, n_scales, coeffs,
+              op_scale, op_shift, normalize):
+        self.calls.append(f"order{order}.phase{phase}")
+        rows = row_end - row_begin
+        rp, ci = (local if phase == 0 else remote)
+        rp, ci = rp.numpy(), ci.numpy()
+        d = dinv.numpy().astype(np.float64)
+        src = t_prev_local.numpy().astype(np.float64) if phase == 0 else t_prev_full.numpy().astype(np.float64)
+        off = row_begin if phase == 0 else 0
+        acc = np.zeros((rows, f))
+        r = np.repeat(np.arange(rows), np.diff(rp))
+        keep = ci != (r + row_begin)
+        np.add.at(acc, r[keep], d[ci[keep], None] * src[ci[keep] - off])
+        if phase == 0:
+            acc_ws.numpy()[:rows] = acc
+            return
+        acc += acc_ws.numpy()[:rows]
+        di = d[row_begin:row_end, None]
+        theta = (op_scale * (1 - iso.numpy()[row_begin:row_end]) + op_shift)[:, None]
+        xprev = t_prev_local.numpy()[:rows].astype(np.float64)
+        lap = theta * xprev - op_scale * di * acc
+        tk = lap if order == 1 else 2 * lap - t_prev2_local.numpy()[:rows]
+        if t_out_local is not None:
+            t_out_local.numpy()[:rows] = tk
+        o = out_local.numpy()
+        for s in range(n_scales):
+            ck, cp = coeffs[s, order], coeffs[s, order - 1]
+            val = cp * xprev + ck * tk if order == 1 else o[:rows, s, :] + ck * tk
+            if normalize and order == k_max:
+                val = val / (np.abs(val).sum(axis=1, keepdims=True) + 1e-8)
+            o[:rows, s, :] = val
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, f, k, scales, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from efficient_gnn_b200 import sharded, synth
+        from oracle import wats_oracle as orc
+        rp, ci, n = synth.synth_csr(synth.GraphShape("t", 1003, 9000, 3, 21, 1), self_loops=True)
+        part = sharded.RowPartition(n, world)
+        rpl, cil = part.slice_csr(rp, ci, rank)
+        eng = NumpyEngine()
+        sw = sharded.ShardedWavelet(rpl, cil, n, engine=eng, device="cpu")
+        x0 = None
+        x0_full = None
+        if f > 1:
+            x0_full = np.random.default_rng(9).standard_normal((n, f)).astype(np.float32)
+            x0 = torch.from_numpy(x0_full[sw.row_begin:sw.row_end])
+        feats, orders, comb = sw.features(k=k, s=scales, X0_local=x0, return_parts=True)
+        fused = sw.features(k=k, s=scales, X0_local=x0)
+        full = sw.gather_features(fused)
+        adj = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
+        p = orc.wavelet_parts(adj, k=k, s=scales, x0=x0_full)
+        b, e = sw.row_begin, sw.row_end
+        for got, ref in zip(orders, p["T"]):
+            np.testing.assert_allclose(got.numpy(), ref[b:e], atol=2e-5)
+        want = np.concatenate(p["H"], axis=1)
+        np.testing.assert_allclose(feats.numpy(), want[b:e], atol=2e-5)
+        np.testing.assert_allclose(full.numpy(), want, atol=2e-5)
+        # exchange runs between the two halves of every order
+        per_order = [c for c in eng.calls if c.startswith("order") or c in ("fork", "join")]
+        assert per_order[:4] == ["fork", "order1.phase0", "join", "order1.phase1"]
+        # halves partition the shard's entries
+        assert sw.local_half[1].numel() + sw.remote_half[1].numel() == cil.numel()
+        assert bool(((sw.local_half[1] >= b) & (sw.local_half[1] < e)).all())
+        assert not bool(((sw.remote_half[1] >= b) & (sw.remote_half[1] < e)).any())
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,f,k,scales", [(2, 1, 3, 0.8), (2, 3, 4, [0.8, 1.6]), (3, 2, 2, 0.8)])
+def test_sharded_host_logic_gloo(world, f, k, scales):
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, f, k, scales, ret), nprocs=world, join=True)
+    assert [ret.get(r) for r in range(world)] == ["ok"] * world
+
+
+def test_row_partition_and_split():
+    sys.path.insert(0, ROOT)
+    from efficient_gnn_b200 import sharded
+    part = sharded.RowPartition(10, 4)
+    assert [part.begin(r) for r in range(4)] == [0, 3, 6, 9]
+    assert [part.rows(r) for r in range(4)] == [3, 3, 3, 1]
+    part = sharded.RowPartition(3, 8)                      # more ranks than rows
+    assert sum(part.rows(r) for r in range(8)) == 3
+    rowptr = torch.tensor([0, 2, 5, 5], dtype=torch.int32)
+    colidx = torch.tensor([0, 7, 1, 2, 9], dtype=torch.int32)
+    (lp, lc), (rp, rc) = sharded.split_columns(rowptr, colidx, 0, 3)
+    assert lp.tolist() == [0, 1, 3, 3] and lc.tolist() == [0, 1, 2]
+    assert rp.tolist() == [0, 1, 2, 2] and rc.tolist() == [7, 9]
