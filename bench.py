@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--scales", type=int, default=1, help="number of wavelet scales S")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="N>1: do not replay the step as a CUDA graph")
     return ap.parse_args()
 
 

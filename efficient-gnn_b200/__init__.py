@@ -16,6 +16,7 @@ from .wats import (  # noqa: F401
     WATS,
     LaplacianOperator,
     WaveletResult,
+    WaveletSession,
     accuracy,
     chebyshev_polynomials,
     compute_normalized_laplacian,

@@ -357,9 +357,14 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
         gen = torch.Generator(device=dev).manual_seed(sh.seed)
         x0 = torch.randn(n, f, device=dev, generator=gen)[sw.row_begin:sw.row_end].contiguous()
     work = float(nnz) * k_max * f
+    use_graph = not getattr(args, "no_graph", False)
+    from .wats import WaveletSession
+    session = WaveletSession(sw, k=k_max, s=scales, f=f, cuda_graph=use_graph)
+    if x0 is not None:
+        session.x0.copy_(x0)
 
     def step():
-        return sw.features(k=k_max, s=scales, X0_local=x0)
+        return session()
 
     warm = max(3, args.warmup)
     for _ in range(warm):
@@ -369,6 +374,10 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
     sampler = clock_sampler_cls(physical_gpu_index(local_rank))
     sampler.start()
     sw.launches = 0
+    if use_graph:                 # count the launches of one uncaptured pass
+        sw.features(k=k_max, s=scales, X0_local=x0)
+        per_step_launches = sw.launches
+        torch.cuda.synchronize()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     start.record()
@@ -416,7 +425,8 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
                "steps": e_steps,
                "entry": "ShardedWavelet(pinned host row shard) + features -> pinned host, per rank"}
 
-    launches = torch.tensor([sw.launches], device=dev, dtype=torch.float64)
+    launches = torch.tensor([per_step_launches * args.steps if use_graph else sw.launches], device=dev,
+                            dtype=torch.float64)
     dist.all_reduce(launches)
     if rank == 0:
         b_k = algorithmic_bytes(n, nnz, f, k_max, n_scales)
@@ -431,6 +441,7 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
                        "f": f, "self_loops": True,
                        "parallelism": f"{world} row shards, all_gather of the order operand per order (NCCL)",
                        "path": "sell-f1" if (sw.plan is not None and f == 1) else "csr-split-overlap",
+                       "cuda_graph": bool(use_graph),
                        "l2_policy": "per-rank CSR shard %.0f MB; no flush" % (4 * nnz / world / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None,
@@ -439,5 +450,15 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
             "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)
+    # A captured graph keeps NCCL work objects alive; tearing the communicator
+    # down underneath it can block.  Drop the graph first, and leave through
+    # os._exit after a last barrier so no destructor can stall the launcher.
+    del session
+    import gc
+    import sys
+    gc.collect()
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
