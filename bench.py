@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="N>1: do not replay the step as a CUDA graph")
+    ap.add_argument("--check", action="store_true", help="N>1: compare every rank's rows with the single-GPU path")
     return ap.parse_args()
 
 
@@ -278,8 +279,9 @@ def run_ours(args, rank, local_rank, world):
             traffic = json.load(open(tpath)).get(f"{args.workload}_f{f}_k{k_max}_s{n_scales}")
         except Exception:
             traffic = None
+    kernel_name = "sell_spmv_kernel" if (f == 1 and k_max >= 1 and graph.sell_plan() is not None) else "cheb_order_kernel"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "cheb_order_kernel", "peak_source": peak_src,
+                "traffic": traffic, "kernel": kernel_name, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sum(b_k) / k_max, "avg_launch_ms": avg_launch_ms,
                 "per_order_ms": [float(v) for v in order_ms.mean(axis=0)],
                 "order_kernel_share_of_step": float(order_ms.sum(axis=1).mean() / ms_per_step)}

@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libegnn_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 3
 
 # every symbol include/egnn_b200.h declares: name -> (restype, argtypes)
 _P, _I32, _I64, _F32, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -33,7 +33,15 @@ SYMBOLS = {
     "egnn_cheb_wavelet": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, _F32, _F32,
                                     _P, _P, _I32, _P, _P, _P, _I32, _P, _SZ, _P, _P, _P]),
     "egnn_sell_order_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _F32, _F32,
-                                          _I32, _P]),
+                                          _I32, _P, _P]),
+    "egnn_peer_window_bytes": (_SZ, [_I64, _I32, _I32]),
+    "egnn_peer_alloc": (C.c_int, [_SZ, _P, _P]),
+    "egnn_peer_open": (C.c_int, [_P, _P]),
+    "egnn_peer_close": (C.c_int, [_P]),
+    "egnn_peer_free": (C.c_int, [_P]),
+    "egnn_peer_operand": (_P, [_P, _I32]),
+    "egnn_peer_error": (C.c_int, [_P, _P, _P]),
+    "egnn_peer_prescale_push": (C.c_int, [_P, _P, _I64, _I64, _P, _P]),
     "egnn_prescale": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P]),
     "egnn_graph_prep_sharded": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "egnn_cheb_order_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
@@ -48,7 +56,17 @@ class SellPlanStruct(C.Structure):
                 ("n_cols", C.c_int32), ("row0", C.c_int32),
                 ("n_slices", C.c_int64), ("n_vrows", C.c_int64), ("n_entries", C.c_int64), ("n_rowv", C.c_int64),
                 ("slice_off", C.c_void_p), ("blk_slice_ptr", C.c_void_p), ("idx", C.c_void_p),
-                ("rv_ptr", C.c_void_p), ("rv_idx", C.c_void_p), ("vpart", C.c_void_p)]
+                ("rv_ptr", C.c_void_p), ("vslot", C.c_void_p), ("vpart", C.c_void_p)]
+
+
+MAX_RANKS = 16
+IPC_HANDLE_BYTES = 64
+
+
+class PeerWindowStruct(C.Structure):
+    """Mirror of ``egnn_peer_window`` (include/egnn_b200.h)."""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("rows_per", C.c_int64), ("f", C.c_int32),
+                ("reserved", C.c_int32), ("base", C.c_void_p * MAX_RANKS)]
 
 
 class EgnnError(RuntimeError):
@@ -99,11 +117,20 @@ def host_array(ctype, values):
     return arr
 
 
+_device_ok = {}
+
+
 def require_device():
-    """Fail loudly unless a B200-class device is current."""
+    """Fail loudly unless a B200-class device is current.  The answer is cached
+    per device index (the query costs milliseconds)."""
     import torch
     if not torch.cuda.is_available():
         raise EgnnError("efficient-gnn-b200 needs a CUDA device (sm_100a); there is no CPU path")
+    dev = torch.cuda.current_device()
+    hit = _device_ok.get(dev)
+    if hit is not None:
+        return hit
     sm, major, minor = C.c_int32(0), C.c_int32(0), C.c_int32(0)
     check(load().egnn_device_info(C.byref(sm), C.byref(major), C.byref(minor)), "egnn_device_info")
-    return sm.value, major.value, minor.value
+    _device_ok[dev] = (sm.value, major.value, minor.value)
+    return _device_ok[dev]

@@ -2,9 +2,11 @@
 // Host-side driver logic only: argument checks, kernel selection, launches on
 // the caller's stream.  No allocation, no synchronisation, no global state.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "cheb.cuh"
 #include "common.cuh"
+#include "peer.cuh"
 #include "prep.cuh"
 #include "sell.cuh"
 
@@ -99,7 +101,7 @@ static int grid_for(int64_t work_items, int threads) {
 struct SellWs {
     int32_t *seg_start, *seg_cnt, *nv, *u_off, *nvrow, *rv_ptr, *uval, *perm, *vsrc, *vslot, *vrow;
     uint32_t *key, *key_sorted;
-    int32_t *q_ptr, *vp_ptr, *bsp, *slice_sz, *slice_off;
+    int32_t *q_ptr, *vp_ptr, *bsp, *bstride, *slice_sz, *slice_off;
     int64_t* totals;
     void* cub_temp;
     size_t cub_bytes;
@@ -144,6 +146,7 @@ static SellWs sell_ws_layout(void* base, int64_t n, int64_t nnz, int C, int lmax
     w.q_ptr = (int32_t*)take(4 * (C + 1));
     w.vp_ptr = (int32_t*)take(4 * (C + 1));
     w.bsp = (int32_t*)take(4 * (C + 1));
+    w.bstride = (int32_t*)take(4 * (C + 1));
     w.slice_sz = (int32_t*)take(4 * (w.smax + 1));
     w.slice_off = (int32_t*)take(4 * (w.smax + 1));
     w.totals = (int64_t*)take(8 * 8);
@@ -159,10 +162,68 @@ static int sell_check_geometry(int64_t n, int64_t nnz, const egnn_sell_plan* pla
                  "row shard [row0, row0 + n) must lie inside n_cols");
     EGNN_REQUIRE(n >= 1 && n < (int64_t(1) << 31) && nnz >= 0 && nnz < (int64_t(1) << 31), "n/nnz out of range");
     EGNN_REQUIRE(plan->n_blocks >= 1 && plan->n_blocks <= kSellMaxBlocks, "n_blocks out of range");
-    EGNN_REQUIRE(plan->col_block >= 1 && plan->col_block <= 65535, "col_block must fit 16-bit local indices");
+    EGNN_REQUIRE(plan->col_block >= 32 && plan->col_block % 32 == 0 && plan->col_block + kSellZeroSlots <= 65536,
+                 "col_block must be a multiple of 32 that leaves room for the zero slots in 16-bit local indices");
     EGNN_REQUIRE((int64_t)plan->col_block * plan->n_blocks >= plan->n_cols, "column blocks do not cover n_cols");
-    EGNN_REQUIRE(plan->lmax >= 8 && plan->lmax <= 65536 && plan->lmax % 8 == 0, "lmax must be a multiple of 8 in [8, 65536]");
+    EGNN_REQUIRE(plan->lmax >= 8 && plan->lmax <= kSellLmaxCap && plan->lmax % 8 == 0, "lmax must be a multiple of 8 in [8, 256]");
     EGNN_REQUIRE((int64_t)plan->n_blocks * n < (int64_t(1) << 30), "n_blocks * n too large");
+    return EGNN_OK;
+}
+
+static inline size_t peer_slab_stride(const egnn_peer_window* w) {
+    return align_up(sizeof(float) * (size_t)w->world * (size_t)w->rows_per * (size_t)w->f, 256);
+}
+static inline float* peer_operand(const egnn_peer_window* w, int r, int which) {
+    return (float*)((char*)w->base[r] + kPeerHeaderBytes + (size_t)which * peer_slab_stride(w));
+}
+static int peer_check(const egnn_peer_window* w) {
+    EGNN_REQUIRE(w->world >= 1 && w->world <= EGNN_MAX_RANKS && w->rank >= 0 && w->rank < w->world, "bad rank/world");
+    EGNN_REQUIRE(w->rows_per >= 1 && w->f >= 1, "bad window shape");
+    for (int r = 0; r < w->world; ++r) EGNN_REQUIRE(w->base[r] != nullptr, "window of a rank is not mapped");
+    return EGNN_OK;
+}
+static void fill_peer_push(PeerPush& pp, const egnn_peer_window* w, int which, bool has_data, bool wait_first) {
+    pp.world = w->world; pp.rank = w->rank; pp.wait_first = wait_first; pp.has_data = has_data;
+    char* own = (char*)w->base[w->rank];
+    for (int r = 0; r < w->world; ++r) {
+        pp.dst[r] = peer_operand(w, r, which);
+        pp.flag[r] = (unsigned*)((char*)w->base[r] + kPeerFlagsOff) + w->rank;
+    }
+    pp.local_flags = (unsigned*)(own + kPeerFlagsOff);
+    pp.epoch = (unsigned*)(own + kPeerEpochOff);
+    pp.done_ctr = (unsigned*)(own + kPeerDoneOff);
+    pp.error = (unsigned*)(own + kPeerErrorOff);
+}
+
+// The narrow-path SpMV: 8 x 16-byte index loads in flight per lane.  `win`
+// non-NULL: the operand is this rank's exchange window (wait for the peers first).
+static int launch_sell_spmv(const egnn_sell_plan* pl, const float* y, int n_cols, cudaStream_t st,
+                            const egnn_peer_window* win = nullptr, int which = 0) {
+    const size_t smem = sizeof(float) * ((size_t)pl->col_block + kSellZeroSlots);
+    int sms = kSmCountB200, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    SellPeerWait pw{};
+    if (win && win->world > 1) {
+        char* own = (char*)win->base[win->rank];
+        pw.local_flags = (const unsigned*)(own + kPeerFlagsOff);
+        pw.epoch = (const unsigned*)(own + kPeerEpochOff);
+        pw.error = (unsigned*)(own + kPeerErrorOff);
+        pw.world = win->world; pw.rank = win->rank;
+        int rc = check_cuda(cudaFuncSetAttribute(sell_spmv_kernel<kSellUnroll, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem), "cudaFuncSetAttribute(sell_spmv_kernel)");
+        if (rc) return rc;
+        sell_spmv_kernel<kSellUnroll, true><<<sms, kSellThreads, smem, st>>>(
+            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->n_blocks, pl->col_block, (int)pl->n_slices,
+            peer_operand(win, win->rank, which), n_cols, pl->vpart, pw);
+    } else {
+        int rc = check_cuda(cudaFuncSetAttribute(sell_spmv_kernel<kSellUnroll, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem), "cudaFuncSetAttribute(sell_spmv_kernel)");
+        if (rc) return rc;
+        sell_spmv_kernel<kSellUnroll, false><<<sms, kSellThreads, smem, st>>>(
+            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->n_blocks, pl->col_block, (int)pl->n_slices,
+            y, n_cols, pl->vpart, pw);
+    }
+    EGNN_LAUNCH_CHECK("sell_spmv_kernel launch");
     return EGNN_OK;
 }
 
@@ -178,7 +239,7 @@ using namespace egnn;
 
 extern "C" {
 
-int egnn_abi_version(void) { return 1; }
+int egnn_abi_version(void) { return 3; }
 
 const char* egnn_last_error(void) { return last_error_buf(); }
 
@@ -350,17 +411,12 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
     if (sell_plan) {
         EGNN_REQUIRE(f == 1 && vals_or_null == nullptr, "the SELL plan serves F = 1 on a binary adjacency");
         EGNN_REQUIRE(sell_plan->n == n && sell_plan->n_cols == n && sell_plan->row0 == 0 && sell_plan->vpart && sell_plan->slice_off && sell_plan->blk_slice_ptr &&
-                     sell_plan->rv_ptr, "SELL plan does not match the graph or is not filled");
+                     sell_plan->rv_ptr && sell_plan->vslot, "SELL plan does not match the graph or is not filled");
         SellEpilogueParams ep{};
         ep.delta = p.delta;
-        ep.rv_ptr = sell_plan->rv_ptr; ep.rv_idx = sell_plan->rv_idx; ep.vpart = sell_plan->vpart;
+        ep.rv_ptr = sell_plan->rv_ptr; ep.vpart = sell_plan->vpart;
         ep.dinv = dinv; ep.iso = iso; ep.out = out; ep.n = (int32_t)n; ep.S = n_scales; ep.row0 = 0;
         ep.a = op_scale; ep.b = op_shift;
-        const size_t smem = sizeof(float) * ((size_t)sell_plan->col_block + 1);
-        rc = check_cuda(cudaFuncSetAttribute(sell_spmv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                        "cudaFuncSetAttribute(sell_spmv_kernel)");
-        if (rc) return rc;
-        const int n_cta = device_sm_count();
         const float* t_prev = x0;
         const float* t_prev2 = nullptr;
         for (int order = 1; order <= k; ++order) {
@@ -377,10 +433,8 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
                 if (rc) return rc;
             }
             if (sell_plan->n_slices > 0) {
-                sell_spmv_kernel<4><<<n_cta, kSellThreads, smem, st>>>(
-                    sell_plan->idx, sell_plan->slice_off, sell_plan->blk_slice_ptr, sell_plan->n_blocks,
-                    sell_plan->col_block, (int)sell_plan->n_slices, y_prev, (int)n, sell_plan->vpart);
-                EGNN_LAUNCH_CHECK("sell_spmv_kernel launch");
+                rc = launch_sell_spmv(sell_plan, y_prev, (int)n, st);
+                if (rc) return rc;
             }
             if (order_events_host) {
                 rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1) + 1], st), "event record");
@@ -513,7 +567,7 @@ int egnn_sell_geometry(int64_t n, int64_t nnz, int32_t* n_blocks, int32_t* col_b
     const int64_t cb_max = 49152;                     // 192 KB of float32 operand per CTA
     int64_t c = ceil_div64(n, cb_max);
     int64_t cb = ceil_div64(ceil_div64(n, c), 32) * 32;
-    if (cb > 65535) cb = 65535 / 32 * 32;
+    if (cb > 65504) cb = 65504;
     *n_blocks = (int32_t)ceil_div64(n, cb);
     *col_block = (int32_t)cb;
     *lmax = 256;
@@ -557,9 +611,9 @@ int egnn_sell_prepare(const int32_t* rowptr, const int32_t* colidx, int64_t n, i
     tb = w.cub_bytes;
     rc = check_cuda(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.key, w.key_sorted, w.uval, w.perm, (int)w.umax, 0, 32, st), "sort vrows");
     if (rc) return rc;
-    sell_blocks_kernel<<<1, 32, 0, st>>>((int)n, C, w.u_off, w.q_ptr, w.vp_ptr, w.bsp, w.totals);
+    sell_blocks_kernel<<<1, 32, 0, st>>>((int)n, C, w.u_off, w.q_ptr, w.vp_ptr, w.bsp, w.bstride, w.totals);
     EGNN_LAUNCH_CHECK("sell_blocks_kernel launch");
-    sell_slice_kernel<<<(unsigned)ceil_div64(w.smax, 256), 256, 0, st>>>(C, lmax, w.key_sorted, w.q_ptr, w.bsp, w.totals, w.slice_sz);
+    sell_slice_kernel<<<(unsigned)ceil_div64(w.smax, 256), 256, 0, st>>>(C, lmax, w.key_sorted, w.q_ptr, w.bsp, w.bstride, w.totals, w.slice_sz);
     EGNN_LAUNCH_CHECK("sell_slice_kernel launch");
     tb = w.cub_bytes;
     rc = check_cuda(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, w.slice_sz, w.slice_off, (int)(w.smax + 1), st), "scan slices"); if (rc) return rc;
@@ -583,7 +637,7 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
     (void)rowptr;
     EGNN_REQUIRE(plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr, "plan buffers not allocated");
     EGNN_REQUIRE(plan->n_entries == 0 || plan->idx, "plan idx not allocated");
-    EGNN_REQUIRE(plan->n_rowv == 0 || plan->rv_idx, "plan rv_idx not allocated");
+    EGNN_REQUIRE(plan->n_vrows == 0 || plan->vslot, "plan vslot not allocated");
     const int C = plan->n_blocks, CB = plan->col_block, lmax = plan->lmax;
     SellWs w = sell_ws_layout(workspace, n, nnz, C, lmax);
     if (!workspace || workspace_bytes < w.total_bytes) {
@@ -595,9 +649,12 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
     rc = check_cuda(cudaMemcpyAsync(plan->blk_slice_ptr, w.bsp, 4 * (C + 1), cudaMemcpyDeviceToDevice, st), "copy blk_slice_ptr"); if (rc) return rc;
     rc = check_cuda(cudaMemcpyAsync(plan->rv_ptr, w.rv_ptr, 4 * (n + 1), cudaMemcpyDeviceToDevice, st), "copy rv_ptr"); if (rc) return rc;
     if (plan->n_slices > 0) {
-        sell_fill_kernel<<<(unsigned)ceil_div64(plan->n_slices * 32, 256), 256, 0, st>>>(
+        rc = check_cuda(cudaFuncSetAttribute(sell_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSellFillSmem),
+                        "cudaFuncSetAttribute(sell_fill_kernel)");
+        if (rc) return rc;
+        sell_fill_kernel<<<(unsigned)ceil_div64(plan->n_slices, kSellFillWarps), kSellFillWarps * 32, kSellFillSmem, st>>>(
             colidx, C, CB, lmax, (int)plan->n_slices, w.key_sorted, w.perm, w.vsrc, w.vslot, w.vrow, w.q_ptr, w.vp_ptr,
-            w.bsp, w.slice_off, plan->idx, plan->rv_idx, plan->row0);
+            w.bsp, w.bstride, w.slice_off, plan->idx, plan->vslot, plan->row0);
         EGNN_LAUNCH_CHECK("sell_fill_kernel launch");
     }
     return EGNN_OK;
@@ -607,37 +664,124 @@ int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full
                             const uint8_t* iso_full, const float* t_prev_local, const float* t_prev2_local,
                             float* t_out_local, float* y_out_local, float* out_local, int32_t order,
                             int32_t k_max, int32_t n_scales, const float* coeffs_host, float op_scale,
-                            float op_shift, int32_t normalize_l1, egnn_stream_t stream) {
-    EGNN_REQUIRE(plan && y_prev_full && dinv_full && iso_full && t_prev_local && out_local && coeffs_host, "null pointer");
-    EGNN_REQUIRE(plan->vpart && plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr, "SELL plan is not filled");
+                            float op_shift, int32_t normalize_l1, egnn_stream_t stream,
+                            const egnn_peer_window* win) {
+    EGNN_REQUIRE(plan && dinv_full && iso_full && t_prev_local && out_local && coeffs_host, "null pointer");
+    EGNN_REQUIRE(win || y_prev_full, "operand missing");
+    EGNN_REQUIRE(plan->vpart && plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr && plan->vslot, "SELL plan is not filled");
     EGNN_REQUIRE(order >= 1 && order <= k_max && k_max <= EGNN_MAX_ORDER, "bad order");
     EGNN_REQUIRE(n_scales >= 1 && n_scales <= EGNN_MAX_SCALES, "n_scales out of range");
     EGNN_REQUIRE(order == 1 || t_prev2_local, "T_{k-2} missing");
-    if (plan->n == 0) return EGNN_OK;
+    if (win) {
+        int rc = peer_check(win);
+        if (rc) return rc;
+        EGNN_REQUIRE(win->f == 1 && (int64_t)win->world * win->rows_per >= plan->n_cols &&
+                     (int64_t)plan->row0 + plan->n <= (int64_t)win->world * win->rows_per, "window does not fit the plan");
+    }
+    const bool fused = win && win->world > 1;
+    if (plan->n == 0 && !fused) return EGNN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = sizeof(float) * ((size_t)plan->col_block + 1);
-    int rc = check_cuda(cudaFuncSetAttribute(sell_spmv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                        "cudaFuncSetAttribute(sell_spmv_kernel)");
-    if (rc) return rc;
-    if (plan->n_slices > 0) {
-        sell_spmv_kernel<4><<<device_sm_count(), kSellThreads, smem, st>>>(
-            plan->idx, plan->slice_off, plan->blk_slice_ptr, plan->n_blocks, plan->col_block, (int)plan->n_slices,
-            y_prev_full, plan->n_cols, plan->vpart);
-        EGNN_LAUNCH_CHECK("sell_spmv_kernel launch");
+    const float* operand = win ? peer_operand(win, win->rank, (order - 1) & 1) : y_prev_full;
+    if (plan->n_slices > 0 || fused) {
+        int rc = launch_sell_spmv(plan, operand, plan->n_cols, st, win, (order - 1) & 1);
+        if (rc) return rc;
     }
     SellEpilogueParams ep{};
     ep.delta.n = 0;
-    ep.rv_ptr = plan->rv_ptr; ep.rv_idx = plan->rv_idx; ep.vpart = plan->vpart; ep.y_prev = y_prev_full;
+    ep.rv_ptr = plan->rv_ptr; ep.vpart = plan->vpart; ep.y_prev = operand;
     ep.dinv = dinv_full; ep.iso = iso_full; ep.tprev = t_prev_local; ep.tprev2 = t_prev2_local;
-    ep.tk = t_out_local; ep.y_out = y_out_local; ep.out = out_local;
+    ep.tk = t_out_local; ep.y_out = win ? nullptr : y_out_local; ep.out = out_local;
     ep.n = plan->n; ep.S = n_scales; ep.first = order == 1; ep.normalize = (order == k_max) && normalize_l1;
     ep.row0 = plan->row0; ep.a = op_scale; ep.b = op_shift;
     for (int s = 0; s < n_scales; ++s) {
         ep.c_prev[s] = coeffs_host[s * (k_max + 1) + order - 1];
         ep.c_k[s] = coeffs_host[s * (k_max + 1) + order];
     }
-    sell_epilogue_kernel<<<(unsigned)ceil_div64(plan->n, 256), 256, 0, st>>>(ep);
+    if (win) {
+        fill_peer_push(ep.peer, win, order & 1, order < k_max, false);
+        if (win->world == 1 && order < k_max) ep.y_out = peer_operand(win, 0, order & 1);   // single rank: plain store
+    }
+    const unsigned blocks = (unsigned)ceil_div64(plan->n > 0 ? plan->n : 1, 256);
+    sell_epilogue_kernel<<<blocks, 256, 0, st>>>(ep);
     EGNN_LAUNCH_CHECK("sell_epilogue_kernel launch");
+    return EGNN_OK;
+}
+
+size_t egnn_peer_window_bytes(int64_t rows_per, int32_t world, int32_t f) {
+    if (rows_per < 1 || world < 1 || f < 1) return 0;
+    egnn_peer_window w{};
+    w.world = world; w.rows_per = rows_per; w.f = f;
+    return kPeerHeaderBytes + 2 * peer_slab_stride(&w);
+}
+
+int egnn_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out) {
+    EGNN_REQUIRE(dev_ptr && ipc_handle_out && bytes >= kPeerHeaderBytes, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == EGNN_IPC_HANDLE_BYTES, "IPC handle size");
+    void* ptr = nullptr;
+    int rc = check_cuda(cudaMalloc(&ptr, bytes), "cudaMalloc(exchange window)");
+    if (rc) return rc;
+    rc = check_cuda(cudaMemset(ptr, 0, bytes), "cudaMemset(exchange window)");
+    if (rc) { cudaFree(ptr); return rc; }
+    cudaIpcMemHandle_t h;
+    rc = check_cuda(cudaIpcGetMemHandle(&h, ptr), "cudaIpcGetMemHandle");
+    if (rc) { cudaFree(ptr); return rc; }
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    *dev_ptr = ptr;
+    return EGNN_OK;
+}
+
+int egnn_peer_open(const void* ipc_handle, void** dev_ptr) {
+    EGNN_REQUIRE(ipc_handle && dev_ptr, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    void* ptr = nullptr;
+    int rc = check_cuda(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    if (rc) return rc;
+    *dev_ptr = ptr;
+    return EGNN_OK;
+}
+
+int egnn_peer_close(void* dev_ptr) {
+    EGNN_REQUIRE(dev_ptr != nullptr, "null pointer");
+    return check_cuda(cudaIpcCloseMemHandle(dev_ptr), "cudaIpcCloseMemHandle");
+}
+
+int egnn_peer_free(void* dev_ptr) {
+    EGNN_REQUIRE(dev_ptr != nullptr, "null pointer");
+    return check_cuda(cudaFree(dev_ptr), "cudaFree(exchange window)");
+}
+
+void* egnn_peer_operand(const egnn_peer_window* win, int32_t which) {
+    if (!win || which < 0 || which > 1 || win->rank < 0 || win->rank >= EGNN_MAX_RANKS || !win->base[win->rank]) return nullptr;
+    return peer_operand(win, win->rank, which);
+}
+
+int egnn_peer_error(const egnn_peer_window* win, int32_t* error_out, egnn_stream_t stream) {
+    EGNN_REQUIRE(win && error_out, "null pointer");
+    int rc = peer_check(win);
+    if (rc) return rc;
+    unsigned v = 0;
+    rc = check_cuda(cudaMemcpyAsync(&v, (char*)win->base[win->rank] + kPeerErrorOff, 4, cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)stream), "copy error word");
+    if (rc) return rc;
+    rc = check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "sync");
+    if (rc) return rc;
+    *error_out = (int32_t)v;
+    return EGNN_OK;
+}
+
+int egnn_peer_prescale_push(const float* x_local, const float* dinv_full, int64_t n_rows, int64_t row0,
+                            const egnn_peer_window* win, egnn_stream_t stream) {
+    EGNN_REQUIRE(dinv_full && win, "null pointer");
+    EGNN_REQUIRE(n_rows >= 0 && row0 >= 0 && (n_rows == 0 || x_local), "bad shape");
+    int rc = peer_check(win);
+    if (rc) return rc;
+    EGNN_REQUIRE(win->f == 1 && row0 + n_rows <= (int64_t)win->world * win->rows_per, "window does not fit the rows");
+    PeerPush pp{};
+    fill_peer_push(pp, win, 0, true, true);
+    const int blocks = grid_for(n_rows > 0 ? n_rows : 1, 256);
+    peer_prescale_push_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x_local, dinv_full, n_rows, row0, pp);
+    EGNN_LAUNCH_CHECK("peer_prescale_push_kernel launch");
     return EGNN_OK;
 }
 

@@ -28,6 +28,7 @@
 
 #include "cheb.cuh"
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace egnn {
 
@@ -100,9 +101,19 @@ sell_emit_kernel(int n, int C, int lmax, const int32_t* __restrict__ seg_start,
 }
 
 // ---- build pass 3: block pointers (padded to whole slices) ------------------
+// Slices of a block are stored in a strided order of their length rank (slice
+// t holds the rows of rank (t * stride) mod n_c, stride ~ 0.618 n_c, coprime to
+// n_c): any contiguous range of slices - what one CTA of the hot kernel gets -
+// then carries the same mix of long and short rows, so equal entries mean equal time.
+__device__ __forceinline__ int sell_gcd(int a, int b) {
+    while (b) { const int t = a % b; a = b; b = t; }
+    return a;
+}
+
 __global__ void sell_blocks_kernel(int n, int C, const int32_t* __restrict__ u_off,
                                    int32_t* __restrict__ q_ptr, int32_t* __restrict__ vp_ptr,
-                                   int32_t* __restrict__ blk_slice_ptr, int64_t* __restrict__ totals) {
+                                   int32_t* __restrict__ blk_slice_ptr, int32_t* __restrict__ blk_stride,
+                                   int64_t* __restrict__ totals) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int vp = 0;
     for (int c = 0; c < C; ++c) {
@@ -111,7 +122,12 @@ __global__ void sell_blocks_kernel(int n, int C, const int32_t* __restrict__ u_o
         q_ptr[c] = q0;
         vp_ptr[c] = vp;
         blk_slice_ptr[c] = vp / kSellSliceRows;
-        vp += (q1 - q0 + kSellSliceRows - 1) / kSellSliceRows * kSellSliceRows;
+        const int n_c = (q1 - q0 + kSellSliceRows - 1) / kSellSliceRows;
+        int stride = (int)(0.6180339887 * (double)n_c);
+        if (stride < 1) stride = 1;
+        while (sell_gcd(stride, n_c > 0 ? n_c : 1) != 1) ++stride;
+        blk_stride[c] = stride;
+        vp += n_c * kSellSliceRows;
     }
     q_ptr[C] = u_off[(size_t)C * n];
     vp_ptr[C] = vp;
@@ -127,15 +143,22 @@ __device__ __forceinline__ int sell_block_of_slice(const int32_t* blk_slice_ptr,
     return c;
 }
 
+// length rank (in slices) of the rows stored in slice s of block c
+__device__ __forceinline__ int sell_rank_of_slice(const int32_t* blk_slice_ptr, const int32_t* blk_stride, int c, int s) {
+    const int n_c = blk_slice_ptr[c + 1] - blk_slice_ptr[c];
+    return (int)(((int64_t)(s - blk_slice_ptr[c]) * blk_stride[c]) % n_c);
+}
+
 // ---- build pass 4: padded size of every slice --------------------------------
 __global__ void __launch_bounds__(256)
 sell_slice_kernel(int C, int lmax, const uint32_t* __restrict__ key_sorted,
                   const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ blk_slice_ptr,
-                  const int64_t* __restrict__ totals, int32_t* __restrict__ slice_sz) {
+                  const int32_t* __restrict__ blk_stride, const int64_t* __restrict__ totals,
+                  int32_t* __restrict__ slice_sz) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= (int)totals[kTotSlices]) return;
     const int c = sell_block_of_slice(blk_slice_ptr, C, s);
-    const int rank0 = (s - blk_slice_ptr[c]) * kSellSliceRows;
+    const int rank0 = sell_rank_of_slice(blk_slice_ptr, blk_stride, c, s) * kSellSliceRows;
     const int len = lmax - (int)(key_sorted[q_ptr[c] + rank0] & 0xffffu);     // longest row of the slice
     slice_sz[s] = (len + kSellGroup - 1) / kSellGroup * kSellGroup * kSellSliceRows;
 }
@@ -148,58 +171,130 @@ __global__ void sell_totals_kernel(const int32_t* __restrict__ slice_off, const 
 }
 
 // ---- build pass 5: write the lane-interleaved 16-bit index stream -----------
-__global__ void __launch_bounds__(256)
+// Entry order inside a virtual row is free (the partial sum is a plain sum), so
+// it is chosen to keep the hot kernel's shared-memory gathers off each other's
+// banks: the warp's LDS for position j reads one entry per lane, and lane r
+// wants bank (r + j) mod 32 there.  Every entry goes to a position whose wanted
+// bank is its own (local column mod 32) while such positions last; the
+// overflow takes the free positions in order, and unused positions point at the
+// zero slot of the wanted bank (32 zero slots at CB .. CB+31; stored self loops
+// too).  One warp per slice: the 32 rows are placed one after the other by the
+// whole warp (coalesced reads of the CSR row, match_any for the per-bank
+// ordinals), staged in shared memory and written out with 16-byte stores.
+constexpr int kSellFillWarps = 4;
+constexpr int kSellLmaxCap = 256;          // positions per lane the staging buffer holds
+constexpr int kSellFillWarpHalves = kSellLmaxCap * kSellSliceRows + kSellLmaxCap + 64 + 16;   // stage + ovf + cnt + occ (uint16 units)
+constexpr size_t kSellFillSmem = (size_t)kSellFillWarps * kSellFillWarpHalves * sizeof(uint16_t);
+
+__global__ void __launch_bounds__(kSellFillWarps * 32)
 sell_fill_kernel(const int32_t* __restrict__ colidx, int C, int CB, int lmax, int n_slices,
                  const uint32_t* __restrict__ key_sorted, const int32_t* __restrict__ perm,
-                 const int32_t* __restrict__ vsrc, const int32_t* __restrict__ vslot,
+                 const int32_t* __restrict__ vsrc, const int32_t* __restrict__ vslot_u,
                  const int32_t* __restrict__ vrow, const int32_t* __restrict__ q_ptr,
                  const int32_t* __restrict__ vp_ptr, const int32_t* __restrict__ blk_slice_ptr,
-                 const int32_t* __restrict__ slice_off, uint16_t* __restrict__ idx,
-                 int32_t* __restrict__ rv_idx, int row0) {
+                 const int32_t* __restrict__ blk_stride, const int32_t* __restrict__ slice_off,
+                 uint16_t* __restrict__ idx, int32_t* __restrict__ vslot_out, int row0) {
+    extern __shared__ __align__(16) uint16_t fill_smem[];
     const int lane = threadIdx.x & 31;
-    const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int wid = threadIdx.x >> 5;
+    const int s = blockIdx.x * kSellFillWarps + wid;
     if (s >= n_slices) return;
+    uint16_t* stage = fill_smem + (size_t)wid * kSellFillWarpHalves;
+    uint16_t* ovf = stage + kSellLmaxCap * kSellSliceRows;
+    int* cnt = reinterpret_cast<int*>(ovf + kSellLmaxCap);            // [32] entries seen per bank
+    unsigned* occ = reinterpret_cast<unsigned*>(cnt + 32);            // [8] occupied positions
+    const unsigned lt_mask = (1u << lane) - 1u;
+
     const int c = sell_block_of_slice(blk_slice_ptr, C, s);
-    const int v = s * kSellSliceRows + lane;
-    const int rank = v - vp_ptr[c];
+    const int v = s * kSellSliceRows + lane;                          // storage slot of this lane's virtual row
+    const int rank = sell_rank_of_slice(blk_slice_ptr, blk_stride, c, s) * kSellSliceRows + lane;
     const bool valid = rank < (q_ptr[c + 1] - q_ptr[c]);
-    int len = 0, src = 0, row = -1;
+    int len = 0, src = 0, row = -1, slot = -1;
     if (valid) {
         const int q = q_ptr[c] + rank;
         const int u = perm[q];
         len = lmax - (int)(key_sorted[q] & 0xffffu);
         src = vsrc[u];
         row = vrow[u] + row0;             // global id of the row (diagonal test)
-        rv_idx[vslot[u]] = v;
+        slot = vslot_u[u];
     }
+    vslot_out[v] = slot;                  // -1: padding lane of the block's last slice
     const int off = slice_off[s];
-    const int groups = (slice_off[s + 1] - off) / (kSellGroup * kSellSliceRows);
+    const int lpad = (slice_off[s + 1] - off) / kSellSliceRows;      // positions per lane
     const int col0 = c * CB;
-    uint4* dst = reinterpret_cast<uint4*>(idx + off) + lane;
-    for (int g = 0; g < groups; ++g) {
-        uint32_t w[4];
+
+    // the CSR entries of row r+1 are fetched (coalesced, <= 8 x 32) while row r is placed
+    constexpr int kBatches = kSellLmaxCap / 32;
+    int cols_next[kBatches];
+    {
+        const int l0 = __shfl_sync(0xffffffffu, len, 0), s0 = __shfl_sync(0xffffffffu, src, 0);
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            uint32_t pair = 0;
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int j = g * kSellGroup + h * 2 + t;
-                uint32_t loc = (uint32_t)CB;                      // zero slot: padding and self loops
-                if (j < len) {
-                    const int col = __ldg(colidx + src + j);
-                    if (col != row) loc = (uint32_t)(col - col0);
-                }
-                pair |= loc << (16 * t);
-            }
-            w[h] = pair;
-        }
-        dst[(size_t)g * kSellSliceRows] = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int t = 0; t < kBatches; ++t) cols_next[t] = (t * 32 + lane < l0) ? __ldg(colidx + s0 + t * 32 + lane) : -1;
     }
+    for (int r = 0; r < kSellSliceRows; ++r) {
+        const int r_len = __shfl_sync(0xffffffffu, len, r);
+        const int r_row = __shfl_sync(0xffffffffu, row, r);
+        int cols[kBatches];
+#pragma unroll
+        for (int t = 0; t < kBatches; ++t) cols[t] = cols_next[t];
+        if (r + 1 < kSellSliceRows) {
+            const int l1 = __shfl_sync(0xffffffffu, len, r + 1), s1 = __shfl_sync(0xffffffffu, src, r + 1);
+#pragma unroll
+            for (int t = 0; t < kBatches; ++t) cols_next[t] = (t * 32 + lane < l1) ? __ldg(colidx + s1 + t * 32 + lane) : -1;
+        }
+        uint16_t* mine = stage + r * kSellGroup;                      // position j -> mine[(j >> 3) * 256 + (j & 7)]
+        cnt[lane] = 0;
+        if (lane < kSellLmaxCap / 32) occ[lane] = 0u;
+        __syncwarp();
+        int n_ovf = 0;
+#pragma unroll
+        for (int t = 0; t < kBatches; ++t) {
+            if (t * 32 < r_len) {                                     // warp-uniform
+                const int col = cols[t];
+                const int loc = (col >= 0 && col != r_row) ? col - col0 : -1;
+                const bool act = loc >= 0;
+                const int b = loc & 31;
+                const unsigned grp = __match_any_sync(0xffffffffu, act ? b : 32 + lane);
+                const int rank_in = __popc(grp & lt_mask);
+                const int base = act ? cnt[b] : 0;
+                __syncwarp();
+                if (act && rank_in == 0) cnt[b] = base + __popc(grp);
+                const int j = ((b - r) & 31) + 32 * (base + rank_in);
+                const bool placed = act && j < lpad;
+                if (placed) {
+                    mine[(j >> 3) * (kSellGroup * kSellSliceRows) + (j & 7)] = (uint16_t)loc;
+                    atomicOr(&occ[j >> 5], 1u << (j & 31));
+                }
+                const unsigned om = __ballot_sync(0xffffffffu, act && !placed);
+                if (act && !placed) ovf[n_ovf + __popc(om & lt_mask)] = (uint16_t)loc;
+                n_ovf += __popc(om);
+                __syncwarp();
+            }
+        }
+        int taken = 0;
+        for (int w = 0; w * 32 < lpad; ++w) {
+            const int p = w * 32 + lane;
+            const bool is_free = p < lpad && !((occ[w] >> lane) & 1u);
+            const unsigned fm = __ballot_sync(0xffffffffu, is_free);
+            if (is_free) {
+                const int kth = taken + __popc(fm & lt_mask);
+                mine[(p >> 3) * (kSellGroup * kSellSliceRows) + (p & 7)] =
+                    kth < n_ovf ? ovf[kth] : (uint16_t)(CB + ((r + p) & 31));
+            }
+            taken += __popc(fm);
+        }
+        __syncwarp();
+    }
+    const int groups = lpad / kSellGroup;
+    const uint4* st4 = reinterpret_cast<const uint4*>(stage) + lane;
+    uint4* dst = reinterpret_cast<uint4*>(idx + off) + lane;
+    for (int g = 0; g < groups; ++g) dst[(size_t)g * kSellSliceRows] = st4[g * kSellSliceRows];
 }
 
 // ---- hot kernel ---------------------------------------------------------------
-// y: the gather operand dinv (.) T_{k-1}, [n] float32.  One partial sum per
-// virtual row goes to vpart[V].  Dynamic shared memory: (CB + 1) floats.
+// y: the gather operand dinv (.) T_{k-1}, [n] float32.  The partial sum of
+// virtual row v goes to vpart[vslot[v]] (row-major: a row's partials are
+// contiguous for the epilogue).  Dynamic shared memory: (CB + 32) floats.
 __device__ __forceinline__ uint4 ld_stream_u32x4(const uint4* p) {
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -215,15 +310,30 @@ __device__ __forceinline__ float sell_gather8(const float* ysm, const uint4 q) {
     return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
-template <int UNROLL>
+constexpr int kSellZeroSlots = 32;
+constexpr int kSellUnroll = 8;            // 16-byte index loads in flight per lane (measured best of 2/4/6/8)
+
+// PEER: the operand lives in this rank's exchange window and is written by the
+// other GPUs over NVLink; the CTA first waits for their flags, and stages with
+// L2-coherent loads (ld.global.cg) instead of the non-coherent path.
+struct SellPeerWait {
+    const unsigned* local_flags;
+    const unsigned* epoch;
+    unsigned* error;
+    int32_t world, rank;
+};
+
+template <int UNROLL, bool PEER>
 __global__ void __launch_bounds__(kSellThreads, 1)
 sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ slice_off,
-                 const int32_t* __restrict__ blk_slice_ptr, int C, int CB, int n_slices,
-                 const float* __restrict__ y, int n, float* __restrict__ vpart) {
+                 const int32_t* __restrict__ blk_slice_ptr, const int32_t* __restrict__ vslot,
+                 int C, int CB, int n_slices, const float* y, int n,
+                 float* __restrict__ vpart, const SellPeerWait pw) {
     extern __shared__ __align__(16) float ysm[];
     __shared__ int next_slice;
     __shared__ int range[2];
     const int lane = threadIdx.x & 31;
+    if (PEER) peer_consumer_wait(pw.local_flags, pw.epoch, pw.world, pw.rank, pw.error);
 
     if (threadIdx.x == 0) {
         // even split of the padded entries over the CTAs, on slice boundaries
@@ -263,12 +373,12 @@ sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ s
             const int cnt4 = cnt >> 2;
             const float4* src4 = reinterpret_cast<const float4*>(src);
             float4* dst4 = reinterpret_cast<float4*>(ysm);
-            for (int t = threadIdx.x; t < cnt4; t += kSellThreads) dst4[t] = __ldg(src4 + t);
-            for (int t = (cnt4 << 2) + threadIdx.x; t < cnt; t += kSellThreads) ysm[t] = __ldg(src + t);
+            for (int t = threadIdx.x; t < cnt4; t += kSellThreads) dst4[t] = PEER ? __ldcg(src4 + t) : __ldg(src4 + t);
+            for (int t = (cnt4 << 2) + threadIdx.x; t < cnt; t += kSellThreads) ysm[t] = PEER ? __ldcg(src + t) : __ldg(src + t);
         } else {
-            for (int t = threadIdx.x; t < cnt; t += kSellThreads) ysm[t] = __ldg(src + t);
+            for (int t = threadIdx.x; t < cnt; t += kSellThreads) ysm[t] = PEER ? __ldcg(src + t) : __ldg(src + t);
         }
-        for (int t = cnt + threadIdx.x; t <= CB; t += kSellThreads) ysm[t] = 0.f;     // includes the zero slot
+        for (int t = cnt + threadIdx.x; t < CB + kSellZeroSlots; t += kSellThreads) ysm[t] = 0.f;   // includes the zero slots
         if (threadIdx.x == 0) next_slice = sub_begin;
         __syncthreads();
 
@@ -279,6 +389,7 @@ sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ s
             if (s >= sub_end) break;
             const int off = __ldg(slice_off + s);
             const int groups = (__ldg(slice_off + s + 1) - off) / (kSellGroup * kSellSliceRows);
+            const int slot = __ldg(vslot + (size_t)s * kSellSliceRows + lane);
             const uint4* p = reinterpret_cast<const uint4*>(idx + off) + lane;
             float acc0 = 0.f, acc1 = 0.f;
             int g = 0;
@@ -293,7 +404,7 @@ sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ s
                 }
             }
             for (; g < groups; ++g) acc0 += sell_gather8(ysm, ld_stream_u32x4(p + (size_t)g * kSellSliceRows));
-            vpart[(size_t)s * kSellSliceRows + lane] = acc0 + acc1;
+            if (slot >= 0) vpart[slot] = acc0 + acc1;
         }
     }
 }
@@ -301,8 +412,7 @@ sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ s
 // ---- per-row epilogue -----------------------------------------------------------
 struct SellEpilogueParams {
     const int32_t* rv_ptr;
-    const int32_t* rv_idx;
-    const float* vpart;
+    const float* vpart;      // row-major partial sums: row i owns [rv_ptr[i], rv_ptr[i+1])
     const float* y_prev;     // gather operand (for the edge flips)
     const float* dinv;
     const uint8_t* iso;
@@ -317,17 +427,15 @@ struct SellEpilogueParams {
     float c_prev[EGNN_MAX_SCALES];
     float c_k[EGNN_MAX_SCALES];
     DeltaList delta;
+    PeerPush peer;           // world > 1: dinv (.) T_k goes into every rank's exchange window
 };
 
-__global__ void __launch_bounds__(256)
-sell_epilogue_kernel(const __grid_constant__ SellEpilogueParams p) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
+__device__ __forceinline__ void sell_epilogue_row(const SellEpilogueParams& p, int i) {
     // a hub row owns hundreds of virtual rows: add their partials in float64,
     // always in the same order (deterministic)
     double accd = 0.0;
     const int e = __ldg(p.rv_ptr + i + 1);
-    for (int t = __ldg(p.rv_ptr + i); t < e; ++t) accd += (double)__ldg(p.vpart + __ldg(p.rv_idx + t));
+    for (int t = __ldg(p.rv_ptr + i); t < e; ++t) accd += (double)p.vpart[t];
     for (int d = 0; d < p.delta.n; ++d)
         if (p.delta.row[d] == i + p.row0 && p.delta.col[d] != i + p.row0)
             accd += (double)p.delta.val[d] * (double)__ldg(p.y_prev + p.delta.col[d]);
@@ -340,12 +448,23 @@ sell_epilogue_kernel(const __grid_constant__ SellEpilogueParams p) {
     const float tk = p.first ? lap : fmaf(2.f, lap, -p.tprev2[i]);
     if (p.tk) p.tk[i] = tk;
     if (p.y_out) p.y_out[i] = di * tk;
+    if (p.peer.world > 1 && p.peer.has_data) {
+        const float yv = di * tk;
+        for (int r = 0; r < p.peer.world; ++r) p.peer.dst[r][p.row0 + i] = yv;
+    }
     for (int s = 0; s < p.S; ++s) {
         float o = p.first ? fmaf(p.c_k[s], tk, p.c_prev[s] * xprev)
                           : fmaf(p.c_k[s], tk, p.out[(size_t)i * p.S + s]);
         if (p.normalize) o = o / (fabsf(o) + 1e-8f);
         p.out[(size_t)i * p.S + s] = o;
     }
+}
+
+__global__ void __launch_bounds__(256)
+sell_epilogue_kernel(const __grid_constant__ SellEpilogueParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.n) sell_epilogue_row(p, i);
+    peer_producer_signal(p.peer);
 }
 
 }  // namespace egnn

@@ -168,28 +168,7 @@ class CsrGraph:
             return None
         if bool(self._unsorted_flag.item()):
             return None
-        dev = self.device
-        with torch.cuda.device(dev):
-            plan = _cabi.SellPlanStruct()
-            plan.n, plan.n_blocks, plan.col_block, plan.lmax = self.n, nb.value, cb.value, lmax.value
-            plan.n_cols, plan.row0 = self.n, 0
-            ws_bytes = int(lib.egnn_sell_ws_bytes(self.n, self.nnz, nb.value, lmax.value))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            _cabi.check(lib.egnn_sell_prepare(_cabi.ptr(self.rowptr), _cabi.ptr(self.colidx), self.n, self.nnz,
-                                              C.byref(plan), _cabi.ptr(ws), ws_bytes, _stream()), "egnn_sell_prepare")
-            bufs = {
-                "slice_off": torch.empty(plan.n_slices + 1, dtype=torch.int32, device=dev),
-                "blk_slice_ptr": torch.empty(plan.n_blocks + 1, dtype=torch.int32, device=dev),
-                "idx": torch.empty(max(1, plan.n_entries), dtype=torch.int16, device=dev),
-                "rv_ptr": torch.empty(self.n + 1, dtype=torch.int32, device=dev),
-                "rv_idx": torch.empty(max(1, plan.n_rowv), dtype=torch.int32, device=dev),
-                "vpart": torch.empty(max(1, plan.n_vrows), dtype=torch.float32, device=dev),
-            }
-            for name, t in bufs.items():
-                setattr(plan, name, t.data_ptr())
-            _cabi.check(lib.egnn_sell_fill(_cabi.ptr(self.rowptr), _cabi.ptr(self.colidx), self.n, self.nnz,
-                                           C.byref(plan), _cabi.ptr(ws), ws_bytes, _stream()), "egnn_sell_fill")
-        plan._keepalive = bufs
+        plan = build_sell_plan(self.rowptr, self.colidx, self.n, self.n, 0, (nb.value, cb.value, lmax.value))
         self._sell = plan
         return plan
 
@@ -218,6 +197,39 @@ class CsrGraph:
         data = np.ones(self.nnz, np.float32) if self.vals is None else self.vals.cpu().numpy()
         return sp.csr_matrix((data, self.colidx.cpu().numpy(), self.rowptr.cpu().numpy()),
                              shape=(self.n, self.n))
+
+
+def build_sell_plan(rowptr: torch.Tensor, colidx: torch.Tensor, n_rows: int, n_cols: int, row0: int, geometry):
+    """Build the SELL plan of ``n_rows`` CSR rows (a whole graph or a row shard
+    starting at global row ``row0``) over ``n_cols`` columns: prepare (counts,
+    one stream synchronisation), allocate the plan arrays as torch tensors,
+    fill.  ``geometry`` = (n_blocks, col_block, lmax) from egnn_sell_geometry."""
+    lib = _cabi.load()
+    dev = rowptr.device
+    nnz = int(colidx.numel())
+    nb, cb, lmax = geometry
+    with torch.cuda.device(dev):
+        plan = _cabi.SellPlanStruct()
+        plan.n, plan.n_blocks, plan.col_block, plan.lmax = n_rows, nb, cb, lmax
+        plan.n_cols, plan.row0 = n_cols, row0
+        ws_bytes = int(lib.egnn_sell_ws_bytes(n_rows, nnz, nb, lmax))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _cabi.check(lib.egnn_sell_prepare(_cabi.ptr(rowptr), _cabi.ptr(colidx), n_rows, nnz,
+                                          C.byref(plan), _cabi.ptr(ws), ws_bytes, _stream()), "egnn_sell_prepare")
+        bufs = {
+            "slice_off": torch.empty(plan.n_slices + 1, dtype=torch.int32, device=dev),
+            "blk_slice_ptr": torch.empty(plan.n_blocks + 1, dtype=torch.int32, device=dev),
+            "idx": torch.empty(max(1, plan.n_entries), dtype=torch.int16, device=dev),
+            "rv_ptr": torch.empty(n_rows + 1, dtype=torch.int32, device=dev),
+            "vslot": torch.empty(max(1, plan.n_vrows), dtype=torch.int32, device=dev),
+            "vpart": torch.empty(max(1, plan.n_rowv), dtype=torch.float32, device=dev),
+        }
+        for name, t in bufs.items():
+            setattr(plan, name, t.data_ptr())
+        _cabi.check(lib.egnn_sell_fill(_cabi.ptr(rowptr), _cabi.ptr(colidx), n_rows, nnz,
+                                       C.byref(plan), _cabi.ptr(ws), ws_bytes, _stream()), "egnn_sell_fill")
+    plan._keepalive = bufs
+    return plan
 
 
 def as_graph(adj, device="cuda") -> CsrGraph:

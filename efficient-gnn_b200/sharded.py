@@ -33,7 +33,7 @@ import torch.distributed as dist
 from . import _cabi
 from .wats import heat_coefficients
 
-__all__ = ["RowPartition", "split_columns", "CudaEngine", "DistComm", "ShardedWavelet"]
+__all__ = ["RowPartition", "split_columns", "CudaEngine", "DistComm", "PeerExchange", "ShardedWavelet"]
 
 
 class RowPartition:
@@ -132,39 +132,24 @@ class CudaEngine:
         _cabi.check(lib.egnn_sell_geometry(n_cols, nnz, C.byref(nb), C.byref(cb), C.byref(lmax)), "egnn_sell_geometry")
         if nnz / (n_rows * nb.value) < self.SELL_MIN_SEGMENT:
             return None
-        plan = _cabi.SellPlanStruct()
-        plan.n, plan.n_blocks, plan.col_block, plan.lmax = n_rows, nb.value, cb.value, lmax.value
-        plan.n_cols, plan.row0 = n_cols, row0
-        ws_bytes = int(lib.egnn_sell_ws_bytes(n_rows, nnz, nb.value, lmax.value))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _cabi.check(lib.egnn_sell_prepare(_cabi.ptr(rowptr), _cabi.ptr(colidx), n_rows, nnz, C.byref(plan),
-                                          _cabi.ptr(ws), ws_bytes, _stream()), "egnn_sell_prepare")
-        bufs = {
-            "slice_off": torch.empty(plan.n_slices + 1, dtype=torch.int32, device=dev),
-            "blk_slice_ptr": torch.empty(plan.n_blocks + 1, dtype=torch.int32, device=dev),
-            "idx": torch.empty(max(1, plan.n_entries), dtype=torch.int16, device=dev),
-            "rv_ptr": torch.empty(n_rows + 1, dtype=torch.int32, device=dev),
-            "rv_idx": torch.empty(max(1, plan.n_rowv), dtype=torch.int32, device=dev),
-            "vpart": torch.empty(max(1, plan.n_vrows), dtype=torch.float32, device=dev),
-        }
-        for name, t in bufs.items():
-            setattr(plan, name, t.data_ptr())
-        _cabi.check(lib.egnn_sell_fill(_cabi.ptr(rowptr), _cabi.ptr(colidx), n_rows, nnz, C.byref(plan),
-                                       _cabi.ptr(ws), ws_bytes, _stream()), "egnn_sell_fill")
-        plan._keepalive = bufs
-        return plan
+        from .graph import build_sell_plan
+        return build_sell_plan(rowptr, colidx, n_rows, n_cols, row0, (nb.value, cb.value, lmax.value))
 
     def prescale(self, x_local, dinv, y_local, n_rows, f, row0):
         _cabi.check(self.lib.egnn_prescale(_cabi.ptr(x_local), _cabi.ptr(dinv), _cabi.ptr(y_local), n_rows, f, row0,
                                            _stream()), "egnn_prescale")
 
     def sell_order(self, plan, y_full, dinv, iso, t_prev, t_prev2, t_out, y_out, out, order, k_max, n_scales,
-                   coeffs, op_scale, op_shift, normalize):
+                   coeffs, op_scale, op_shift, normalize, window=None):
         _cabi.check(self.lib.egnn_sell_order_sharded(
             C.byref(plan), _cabi.ptr(y_full), _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(t_prev), _cabi.ptr(t_prev2),
             _cabi.ptr(t_out), _cabi.ptr(y_out), _cabi.ptr(out), order, k_max, n_scales,
-            coeffs.ctypes.data_as(C.c_void_p), float(op_scale), float(op_shift), 1 if normalize else 0, _stream()),
-            "egnn_sell_order_sharded")
+            coeffs.ctypes.data_as(C.c_void_p), float(op_scale), float(op_shift), 1 if normalize else 0, _stream(),
+            None if window is None else C.byref(window)), "egnn_sell_order_sharded")
+
+    def peer_prescale_push(self, x_local, dinv, n_rows, row0, window):
+        _cabi.check(self.lib.egnn_peer_prescale_push(_cabi.ptr(x_local), _cabi.ptr(dinv), n_rows, row0,
+                                                     C.byref(window), _stream()), "egnn_peer_prescale_push")
 
     # -- stream plumbing ---------------------------------------------------------
     def side_stream(self):
@@ -199,6 +184,69 @@ class DistComm:
             full.copy_(slab)
 
 
+class PeerExchange:
+    """This rank's exchange window plus the peers' windows mapped over CUDA IPC
+    (include/egnn_b200.h ``egnn_peer_window``).  With it an order needs no
+    collective: the epilogue stores the next operand into every rank's window
+    over NVLink and the next SpMV waits on flags (csrc/peer.cuh).  One process
+    per GPU on one node; handles travel through ``torch.distributed``."""
+
+    def __init__(self, rows_per: int, f: int, group=None, device=None):
+        self.lib = _cabi.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _cabi.MAX_RANKS:
+            raise ValueError(f"at most {_cabi.MAX_RANKS} ranks per exchange window")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+        self._opened = []
+        self._own = None
+        with torch.cuda.device(dev):
+            nbytes = int(self.lib.egnn_peer_window_bytes(rows_per, self.world, f))
+            own = C.c_void_p()
+            handle = (C.c_ubyte * _cabi.IPC_HANDLE_BYTES)()
+            _cabi.check(self.lib.egnn_peer_alloc(nbytes, C.byref(own), handle), "egnn_peer_alloc")
+            self._own = own.value
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+            every = torch.empty(self.world * _cabi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            every = every.cpu().numpy().reshape(self.world, _cabi.IPC_HANDLE_BYTES)
+            win = _cabi.PeerWindowStruct()
+            win.rank, win.world, win.rows_per, win.f = self.rank, self.world, int(rows_per), int(f)
+            for r in range(self.world):
+                if r == self.rank:
+                    win.base[r] = self._own
+                    continue
+                buf = (C.c_ubyte * _cabi.IPC_HANDLE_BYTES)(*[int(v) for v in every[r]])
+                mapped = C.c_void_p()
+                _cabi.check(self.lib.egnn_peer_open(buf, C.byref(mapped)), "egnn_peer_open")
+                self._opened.append(mapped.value)
+                win.base[r] = mapped.value
+            self.window = win
+        dist.barrier(group=group)          # every window is zeroed and mapped before anyone stores into it
+        self.group = group
+
+    def error(self) -> int:
+        """Non-zero when a flag wait timed out (synchronises the stream)."""
+        out = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.egnn_peer_error(C.byref(self.window), C.byref(out), _stream()), "egnn_peer_error")
+        return out.value
+
+    def close(self):
+        """Unmap the peers' windows and free this rank's (collective: nobody may
+        still be storing into a window that is being freed)."""
+        if self._own is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                self.lib.egnn_peer_close(C.c_void_p(p))
+            dist.barrier(group=self.group)
+            self.lib.egnn_peer_free(C.c_void_p(self._own))
+        self._opened, self._own = [], None
+
+
 class ShardedWavelet:
     """Wavelet features of a row-sharded graph.
 
@@ -208,7 +256,7 @@ class ShardedWavelet:
     """
 
     def __init__(self, rowptr_local, colidx_local, n_global: int, *, group=None, engine=None, device=None,
-                 use_sell: Optional[bool] = None, comm=None):
+                 use_sell: Optional[bool] = None, comm=None, peer_exchange: Optional[bool] = None):
         self.comm = comm if comm is not None else DistComm(group)
         self.rank, self.world = self.comm.rank, self.comm.world
         self.n = int(n_global)
@@ -228,6 +276,24 @@ class ShardedWavelet:
         self.plan = None
         if use_sell is not False:
             self.plan = self.engine.sell_plan(self.rowptr, self.colidx, self.rows, self.n, self.row_begin, unsorted)
+        # Fused exchange over peer memory for the narrow path: needs real peers
+        # (one process per GPU, NCCL group) and the plan on every rank.
+        self.peer = None
+        real_group = (comm is None and engine is None and self.world > 1 and dist.is_initialized()
+                      and dist.get_backend(group) == "nccl")
+        if isinstance(peer_exchange, PeerExchange):       # reuse an existing window (same partition)
+            if self.plan is None:
+                raise _cabi.EgnnError("a shared exchange window needs the SELL plan on this rank")
+            self.peer, peer_exchange = peer_exchange, False
+        if peer_exchange is None:
+            peer_exchange = real_group and os.environ.get("EGNN_EXCHANGE", "peer") != "nccl"
+        if peer_exchange:
+            if not real_group:
+                raise _cabi.EgnnError("peer exchange needs one process per GPU in an NCCL group")
+            have = torch.tensor([1 if self.plan is not None else 0], device=self.device)
+            dist.all_reduce(have, op=dist.ReduceOp.MIN, group=group)
+            if int(have.item()) == 1:
+                self.peer = PeerExchange(self.part.rows_per, 1, group=group, device=self.device)
         self.launches = 0
 
     # -- collectives -------------------------------------------------------------
@@ -270,7 +336,11 @@ class ShardedWavelet:
         t_prev2 = None
         full = torch.empty((self.world * rp, f), dtype=torch.float32, device=dev)
         use_plan = self.plan is not None and f == 1
-        if use_plan:
+        fused = use_plan and self.peer is not None
+        if fused:
+            eng.peer_prescale_push(t_prev, self.dinv, self.rows, self.row_begin, self.peer.window)
+            self.launches += 1
+        elif use_plan:
             y_slabs = [slab(), slab()]
             if self.rows:
                 eng.prescale(t_prev, self.dinv, y_slabs[0], self.rows, f, self.row_begin)
@@ -286,7 +356,12 @@ class ShardedWavelet:
                 t_out = slab()
             else:
                 t_out = t_prev2               # in place over T_{k-2} (read-then-write per element)
-            if use_plan:
+            if fused:
+                # operand already sits in every rank's window; SpMV waits on flags, epilogue pushes the next one
+                eng.sell_order(self.plan, None, self.dinv, self.iso, t_prev, t_prev2, t_out, None, out, order, k,
+                               n_scales, coeffs, op_scale, op_shift, fused_norm, window=self.peer.window)
+                self.launches += 2
+            elif use_plan:
                 y_prev = y_slabs[(order - 1) & 1]
                 self._allgather(full, y_prev)
                 if self.rows:
@@ -391,6 +466,25 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     dist.barrier()
     ms_per_step = float(ms.item())
+    peer_error = 0 if sw.peer is None else sw.peer.error()
+
+    # optional self-check: every rank also runs the single-GPU path on the whole graph
+    check = None
+    if getattr(args, "check", False):
+        from .graph import CsrGraph
+        from .wats import graph_wavelet_features
+        rp_full, ci_full, _ = synth.synth_csr(args.workload, self_loops=True, device=dev)
+        gfull = CsrGraph(rp_full, ci_full, None, n)
+        x_full = None
+        if f > 1:
+            x_full = torch.randn(n, f, device=dev, generator=torch.Generator(device=dev).manual_seed(sh.seed))
+        want = graph_wavelet_features(gfull, k=k_max, s=scales, X0=x_full)[sw.row_begin:sw.row_end]
+        got = session().clone()
+        diff = torch.tensor([float((got - want).abs().max().item()) if sw.rows else 0.0], device=dev,
+                            dtype=torch.float64)
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        check = {"max_abs_diff_vs_single_gpu": float(diff.item())}
+        del gfull, rp_full, ci_full, want, got
 
     # end to end: pinned host shard -> device -> features -> host, every step
     e2e = None
@@ -400,7 +494,8 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
         out_h = torch.empty((max(1, sw.rows), n_scales * f), dtype=torch.float32).pin_memory()
 
         def e2e_step():
-            g = ShardedWavelet(rp_h.to(dev, non_blocking=True), ci_h.to(dev, non_blocking=True), n, device=dev)
+            g = ShardedWavelet(rp_h.to(dev, non_blocking=True), ci_h.to(dev, non_blocking=True), n, device=dev,
+                               peer_exchange=sw.peer if sw.peer is not None else None)
             xx = None if x0_h is None else x0_h.to(dev, non_blocking=True)
             feats = g.features(k=k_max, s=scales, X0_local=xx)
             out_h[:sw.rows].copy_(feats, non_blocking=True)
@@ -439,14 +534,19 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}-shape", "n": n, "nnz": nnz, "k": k_max, "scales": n_scales,
                        "f": f, "self_loops": True,
-                       "parallelism": f"{world} row shards, all_gather of the order operand per order (NCCL)",
+                       "parallelism": (f"{world} row shards, operand pushed into peer windows over NVLink by the "
+                                       "epilogue kernel, flag wait in the next SpMV (no collective launch)"
+                                       if (sw.peer is not None and f == 1) else
+                                       f"{world} row shards, all_gather of the order operand per order (NCCL)"),
                        "path": "sell-f1" if (sw.plan is not None and f == 1) else "csr-split-overlap",
+                       "exchange": "peer-window" if (sw.peer is not None and f == 1) else "nccl-allgather",
                        "cuda_graph": bool(use_graph),
                        "l2_policy": "per-rank CSR shard %.0f MB; no flush" % (4 * nnz / world / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None,
                          "note": "whole step incl. exchange, aggregate over ranks, compulsory-bytes model"},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()),
+            "exchange_error": int(peer_error), "check": check,
             "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)

@@ -41,6 +41,8 @@ enum egnn_status {
 #define EGNN_MAX_SCALES 8
 #define EGNN_MAX_ORDER 64
 #define EGNN_MAX_DELTA 64
+#define EGNN_MAX_RANKS 16
+#define EGNN_IPC_HANDLE_BYTES 64
 
 /* ABI version of this header (bumped on any signature change). */
 int egnn_abi_version(void);
@@ -111,8 +113,9 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base,
  *   egnn_sell_prepare    counts (all passes but the last) in `workspace`,
  *                        SYNCHRONISES the stream and fills the size fields;
  *   (caller allocates slice_off[n_slices+1], blk_slice_ptr[n_blocks+1],
- *    idx[n_entries] (uint16, 256-byte aligned), rv_ptr[n+1], rv_idx[n_rowv],
- *    vpart[n_vrows] float32 scratch)
+ *    idx[n_entries] (uint16, 256-byte aligned), rv_ptr[n+1], vslot[n_vrows],
+ *    vpart[n_rowv] float32 scratch: row i's partial sums are
+ *    vpart[rv_ptr[i] .. rv_ptr[i+1]), virtual row v writes vpart[vslot[v]])
  *   egnn_sell_fill       writes the index stream; `workspace` must be the
  *                        one prepare used, untouched in between.
  * A plan is read-only afterwards except vpart (one wavelet call at a time). */
@@ -124,7 +127,7 @@ typedef struct egnn_sell_plan {
     int32_t* blk_slice_ptr;
     uint16_t* idx;
     int32_t* rv_ptr;
-    int32_t* rv_idx;
+    int32_t* vslot;
     float* vpart;
 } egnn_sell_plan;
 
@@ -199,24 +202,62 @@ int egnn_cheb_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
                             int32_t normalize_l1, int32_t phase,
                             egnn_stream_t stream);
 
+/* ---- exchange window over peer memory (NVLink / NVSwitch) -------------------
+ * New in this build.  Each rank allocates one window with egnn_peer_alloc
+ * (cudaMalloc, zero-filled, exported as a CUDA IPC handle), the host code
+ * exchanges the 64-byte handles (torch.distributed) and every rank maps the
+ * others' windows with egnn_peer_open.  The sharded order kernels then store
+ * the next order's operand straight into every rank's window and signal with
+ * flags inside it, so an order needs no collective launch (csrc/peer.cuh).
+ * base[r] is rank r's window as mapped in this process (base[rank]: own).   */
+typedef struct egnn_peer_window {
+    int32_t rank, world;
+    int64_t rows_per;            /* rows per rank; the exchanged operand has world * rows_per rows */
+    int32_t f;                   /* its columns */
+    int32_t reserved;
+    void* base[EGNN_MAX_RANKS];
+} egnn_peer_window;
+
+size_t egnn_peer_window_bytes(int64_t rows_per, int32_t world, int32_t f);
+int egnn_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out /* EGNN_IPC_HANDLE_BYTES */);
+int egnn_peer_open(const void* ipc_handle, void** dev_ptr);
+int egnn_peer_close(void* dev_ptr);
+int egnn_peer_free(void* dev_ptr);
+/* Device address of operand buffer `which` (0/1) inside the caller's own window. */
+void* egnn_peer_operand(const egnn_peer_window* win, int32_t which);
+/* Copies the window's error word to *error_out (synchronises `stream`); non-zero
+ * means a flag wait timed out (a peer never arrived).                         */
+int egnn_peer_error(const egnn_peer_window* win, int32_t* error_out, egnn_stream_t stream);
+
 /* One order of the narrow (F = 1) path on a row shard: SELL SpMV over the
  * rank's plan (plan->n rows starting at plan->row0, plan->n_cols columns)
  * against the exchanged full operand y_prev_full = dinv (.) T_{k-1} [n_cols],
  * then the epilogue on the local rows: T_k -> t_out_local (or NULL),
  * dinv (.) T_k -> y_out_local (the slab the next exchange moves; or NULL),
- * scale accumulation into out_local [rows, n_scales].                        */
+ * scale accumulation into out_local [rows, n_scales].
+ * With win_or_null given the exchange is fused: the SpMV waits for the peers'
+ * flags and reads operand buffer (order-1)&1 of the window (y_prev_full is
+ * ignored), the epilogue stores dinv (.) T_k into buffer order&1 of EVERY
+ * rank's window and signals (y_out_local is ignored).                        */
 int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full,
                             const float* dinv_full, const uint8_t* iso_full,
                             const float* t_prev_local, const float* t_prev2_local,
                             float* t_out_local, float* y_out_local, float* out_local,
                             int32_t order, int32_t k_max, int32_t n_scales,
                             const float* coeffs_host, float op_scale, float op_shift,
-                            int32_t normalize_l1, egnn_stream_t stream);
+                            int32_t normalize_l1, egnn_stream_t stream,
+                            const egnn_peer_window* win_or_null);
 
 /* y[r, :] = dinv_full[row0 + r] * x[r, :]: the gather operand of order 1 on
  * the narrow path (later orders get it from the epilogue).                   */
 int egnn_prescale(const float* x, const float* dinv_full, float* y, int64_t n_rows,
                   int32_t f, int64_t row0, egnn_stream_t stream);
+
+/* The same product (F = 1) stored into operand buffer 0 of every rank's
+ * window: first kernel of a fused-exchange step.  It first waits until every
+ * peer has finished the previous step, then stores and signals.             */
+int egnn_peer_prescale_push(const float* x_local, const float* dinv_full, int64_t n_rows,
+                            int64_t row0, const egnn_peer_window* win, egnn_stream_t stream);
 
 /* Degree pass of a row shard (scipy semantics as egnn_graph_prep).  phase 0:
  * row sums of the local rows, their diagonal entries into diag_full[row_begin..]

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_sell.py tests/test_gpu_properties.py -m gpu -q > gpurun_out/pytest_sell.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/pytest_sell.log
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest rc=$?; tail -4 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench.log 2> gpurun_out/bench.err; echo bench rc=$?; python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1])

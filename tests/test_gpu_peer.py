@@ -1,0 +1,96 @@
+"""The fused exchange over peer memory (csrc/peer.cuh) needs one process per
+GPU on >= 2 real GPUs: spin-waiting kernels of different ranks must never share
+a device.  On a single-GPU box only the one-rank window (no peers, plain
+stores) is exercised; the 2-rank cases run under ``gpurun --gpus 2``."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from efficient_gnn_b200 import sharded, synth
+from oracle import wats_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SHAPE = synth.GraphShape("t", 6001, 260_000, 3, 33, 1)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, k, scales, steps, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        rp, ci, n = synth.synth_csr(SHAPE, self_loops=True)
+        part = sharded.RowPartition(n, world)
+        rpl, cil = part.slice_csr(rp, ci, rank)
+        sw = sharded.ShardedWavelet(rpl.to(dev), cil.to(dev), n, device=dev)
+        assert sw.plan is not None and sw.peer is not None, "fused exchange was not selected"
+        outs = []
+        for _ in range(steps):                       # consecutive steps reuse the two operand buffers
+            outs.append(sw.features(k=k, s=scales).cpu().numpy())
+        feats, orders, comb = sw.features(k=k, s=scales, return_parts=True)
+        assert sw.peer.error() == 0, "a flag wait timed out"
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), b=sw.row_begin, e=sw.row_end,
+                 fused=np.stack(outs), comb=comb.cpu().numpy(), **{f"t{i}": o.cpu().numpy() for i, o in enumerate(orders)})
+        sw.peer.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k,scales", [(3, 0.8), (4, [0.8, 1.6]), (1, 0.8)])
+def test_two_rank_fused_exchange_matches_oracle(tmp_path, k, scales):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (one process per GPU)")
+    import torch.multiprocessing as mp
+    world, steps = 2, 3
+    mp.spawn(_worker, args=(world, _free_port(), k, scales, steps, str(tmp_path)), nprocs=world, join=True)
+    rp, ci, n = synth.synth_csr(SHAPE, self_loops=True)
+    adj = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
+    p = orc.wavelet_parts(adj, k=k, s=scales)
+    want_h = np.concatenate(p["H"], axis=1).astype(np.float32)
+    want_s = np.stack(p["S"], axis=1)                                   # [N, S, 1]
+    sure = np.concatenate([np.abs(sj) > 1e-4 * np.abs(sj).max() for sj in p["S"]], axis=1)
+    for rank in range(world):
+        z = np.load(tmp_path / f"rank{rank}.npz")
+        b, e = int(z["b"]), int(z["e"])
+        for i in range(k + 1):
+            ref = p["T"][i]
+            assert np.abs(z[f"t{i}"] - ref[b:e]).max() / np.abs(ref).max() <= 1e-5, f"order {i}"
+        assert np.abs(z["comb"] - want_s[b:e]).max() / np.abs(want_s).max() <= 1e-5
+        for step in range(steps):
+            got = z["fused"][step]
+            np.testing.assert_allclose(got[sure[b:e]], want_h[b:e][sure[b:e]], atol=2e-5)
+        assert np.array_equal(z["fused"][0], z["fused"][-1])           # deterministic across steps
+
+
+def test_single_rank_window_is_a_plain_store(tmp_path):
+    """world == 1: same kernels, no peers, no waits - must equal the NCCL-free path."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()), RANK="0", WORLD_SIZE="1")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    try:
+        rp, ci, n = synth.synth_csr(SHAPE, self_loops=True)
+        plain = sharded.ShardedWavelet(rp.to(dev), ci.to(dev), n, device=dev, peer_exchange=False)
+        peer = sharded.PeerExchange(plain.part.rows_per, 1, device=dev)
+        fused = sharded.ShardedWavelet(rp.to(dev), ci.to(dev), n, device=dev, peer_exchange=peer)
+        a = plain.features(k=3, s=[0.8, 1.6])
+        b = fused.features(k=3, s=[0.8, 1.6])
+        c = fused.features(k=3, s=[0.8, 1.6])
+        assert peer.error() == 0
+        assert torch.equal(a, b) and torch.equal(b, c)
+        peer.close()
+    finally:
+        dist.destroy_process_group()

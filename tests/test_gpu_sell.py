@@ -22,10 +22,11 @@ def decode_plan(g, plan):
     bsp = bufs["blk_slice_ptr"].cpu().numpy()
     idx = bufs["idx"].cpu().numpy().view(np.uint16)
     rv_ptr = bufs["rv_ptr"].cpu().numpy()
-    rv_idx = bufs["rv_idx"].cpu().numpy()
-    vrow_of = np.full(plan.n_vrows, -1, dtype=np.int64)
-    for i in range(g.n):
-        vrow_of[rv_idx[rv_ptr[i]:rv_ptr[i + 1]]] = i
+    vslot = bufs["vslot"].cpu().numpy()[:plan.n_vrows]
+    # virtual row v adds into partial-sum slot vslot[v]; row i owns slots [rv_ptr[i], rv_ptr[i+1])
+    vrow_of = np.where(vslot >= 0, np.searchsorted(rv_ptr, vslot, side="right") - 1, -1)
+    used = vslot[vslot >= 0]
+    assert used.size == plan.n_rowv and np.array_equal(np.sort(used), np.arange(plan.n_rowv))
     rows, cols = [], []
     cb = plan.col_block
     for s in range(plan.n_slices):
@@ -33,7 +34,10 @@ def decode_plan(g, plan):
         seg = idx[slice_off[s]:slice_off[s + 1]].reshape(-1, 32, 8)      # [group, lane, 8]
         for lane in range(32):
             loc = seg[:, lane, :].ravel()
-            loc = loc[loc != cb]
+            want_bank = (lane + np.arange(loc.size)) % 32
+            pads = loc >= cb
+            assert np.all(loc[pads] == cb + want_bank[pads])          # zero slot of the wanted bank
+            loc = loc[~pads]
             v = s * 32 + lane
             if loc.size:
                 assert vrow_of[v] >= 0

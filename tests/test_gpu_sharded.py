@@ -19,8 +19,10 @@ pytestmark = pytest.mark.gpu
 
 
 class ThreadComm:
-    """All ranks live in this process; collectives meet at a barrier.  Every
-    rank issues on the same CUDA stream, so host order = device order."""
+    """All ranks live in this process; collectives meet at a barrier.  The
+    ranks share one device but launch from different threads and side streams,
+    so each collective synchronises the device on both sides (inputs produced
+    before anyone reads them, outputs complete before anyone overwrites)."""
 
     def __init__(self, rank, world, shared):
         self.rank, self.world, self.sh = rank, world, shared
@@ -28,20 +30,24 @@ class ThreadComm:
     def allreduce(self, t):
         sh = self.sh
         sh["parts"][self.rank] = t
+        torch.cuda.synchronize()
         sh["barrier"].wait()
         if self.rank == 0:
             total = torch.stack(sh["parts"]).sum(dim=0)
             for p in sh["parts"]:
                 p.copy_(total)
+            torch.cuda.synchronize()
         sh["barrier"].wait()
 
     def allgather(self, full, slab):
         sh = self.sh
         sh["slabs"][self.rank] = slab
+        torch.cuda.synchronize()
         sh["barrier"].wait()
         rows = slab.shape[0]
         for r in range(self.world):
             full[r * rows:(r + 1) * rows].copy_(sh["slabs"][r])
+        torch.cuda.synchronize()
         sh["barrier"].wait()
 
 
