@@ -53,10 +53,10 @@ SYMBOLS = {
 class SellPlanStruct(C.Structure):
     """Mirror of ``egnn_sell_plan`` (include/egnn_b200.h)."""
     _fields_ = [("n", C.c_int32), ("n_blocks", C.c_int32), ("col_block", C.c_int32), ("lmax", C.c_int32),
-                ("n_cols", C.c_int32), ("row0", C.c_int32),
+                ("n_cols", C.c_int32), ("row0", C.c_int32), ("n_cta", C.c_int32), ("reserved", C.c_int32),
                 ("n_slices", C.c_int64), ("n_vrows", C.c_int64), ("n_entries", C.c_int64), ("n_rowv", C.c_int64),
                 ("slice_off", C.c_void_p), ("blk_slice_ptr", C.c_void_p), ("idx", C.c_void_p),
-                ("rv_ptr", C.c_void_p), ("vslot", C.c_void_p), ("vpart", C.c_void_p)]
+                ("rv_ptr", C.c_void_p), ("vslot", C.c_void_p), ("cta_ptr", C.c_void_p), ("vpart", C.c_void_p)]
 
 
 MAX_RANKS = 16

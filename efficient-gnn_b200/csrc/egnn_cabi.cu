@@ -200,8 +200,7 @@ static void fill_peer_push(PeerPush& pp, const egnn_peer_window* w, int which, b
 static int launch_sell_spmv(const egnn_sell_plan* pl, const float* y, int n_cols, cudaStream_t st,
                             const egnn_peer_window* win = nullptr, int which = 0) {
     const size_t smem = sizeof(float) * ((size_t)pl->col_block + kSellZeroSlots);
-    int sms = kSmCountB200, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = pl->n_cta;
     SellPeerWait pw{};
     if (win && win->world > 1) {
         char* own = (char*)win->base[win->rank];
@@ -213,14 +212,14 @@ static int launch_sell_spmv(const egnn_sell_plan* pl, const float* y, int n_cols
                                                  (int)smem), "cudaFuncSetAttribute(sell_spmv_kernel)");
         if (rc) return rc;
         sell_spmv_kernel<kSellUnroll, true><<<sms, kSellThreads, smem, st>>>(
-            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->n_blocks, pl->col_block, (int)pl->n_slices,
+            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->cta_ptr, pl->n_blocks, pl->col_block,
             peer_operand(win, win->rank, which), n_cols, pl->vpart, pw);
     } else {
         int rc = check_cuda(cudaFuncSetAttribute(sell_spmv_kernel<kSellUnroll, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)smem), "cudaFuncSetAttribute(sell_spmv_kernel)");
         if (rc) return rc;
         sell_spmv_kernel<kSellUnroll, false><<<sms, kSellThreads, smem, st>>>(
-            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->n_blocks, pl->col_block, (int)pl->n_slices,
+            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->cta_ptr, pl->n_blocks, pl->col_block,
             y, n_cols, pl->vpart, pw);
     }
     EGNN_LAUNCH_CHECK("sell_spmv_kernel launch");
@@ -411,7 +410,7 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
     if (sell_plan) {
         EGNN_REQUIRE(f == 1 && vals_or_null == nullptr, "the SELL plan serves F = 1 on a binary adjacency");
         EGNN_REQUIRE(sell_plan->n == n && sell_plan->n_cols == n && sell_plan->row0 == 0 && sell_plan->vpart && sell_plan->slice_off && sell_plan->blk_slice_ptr &&
-                     sell_plan->rv_ptr && sell_plan->vslot, "SELL plan does not match the graph or is not filled");
+                     sell_plan->rv_ptr && sell_plan->vslot && sell_plan->cta_ptr, "SELL plan does not match the graph or is not filled");
         SellEpilogueParams ep{};
         ep.delta = p.delta;
         ep.rv_ptr = sell_plan->rv_ptr; ep.vpart = sell_plan->vpart;
@@ -623,6 +622,7 @@ int egnn_sell_prepare(const int32_t* rowptr, const int32_t* colidx, int64_t n, i
     rc = check_cuda(cudaMemcpyAsync(tot, w.totals, 64, cudaMemcpyDeviceToHost, st), "copy totals"); if (rc) return rc;
     rc = check_cuda(cudaStreamSynchronize(st), "sync"); if (rc) return rc;
     plan->n = (int32_t)n;
+    plan->n_cta = device_sm_count();               // persistent grid of the hot kernel: one CTA per SM
     plan->n_vrows = tot[kTotV];
     plan->n_slices = tot[kTotSlices];
     plan->n_entries = tot[kTotEntries];
@@ -635,7 +635,8 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
     int rc = sell_check_geometry(n, nnz, plan);
     if (rc) return rc;
     (void)rowptr;
-    EGNN_REQUIRE(plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr, "plan buffers not allocated");
+    EGNN_REQUIRE(plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr && plan->cta_ptr, "plan buffers not allocated");
+    EGNN_REQUIRE(plan->n_cta >= 1 && plan->n_cta <= 4096, "n_cta out of range");
     EGNN_REQUIRE(plan->n_entries == 0 || plan->idx, "plan idx not allocated");
     EGNN_REQUIRE(plan->n_vrows == 0 || plan->vslot, "plan vslot not allocated");
     const int C = plan->n_blocks, CB = plan->col_block, lmax = plan->lmax;
@@ -648,6 +649,9 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
     rc = check_cuda(cudaMemcpyAsync(plan->slice_off, w.slice_off, 4 * (plan->n_slices + 1), cudaMemcpyDeviceToDevice, st), "copy slice_off"); if (rc) return rc;
     rc = check_cuda(cudaMemcpyAsync(plan->blk_slice_ptr, w.bsp, 4 * (C + 1), cudaMemcpyDeviceToDevice, st), "copy blk_slice_ptr"); if (rc) return rc;
     rc = check_cuda(cudaMemcpyAsync(plan->rv_ptr, w.rv_ptr, 4 * (n + 1), cudaMemcpyDeviceToDevice, st), "copy rv_ptr"); if (rc) return rc;
+    sell_cta_ranges_kernel<<<(unsigned)ceil_div64(plan->n_cta + 1, 256), 256, 0, st>>>(w.slice_off, (int)plan->n_slices, plan->n_cta,
+                                                                                  plan->cta_ptr);
+    EGNN_LAUNCH_CHECK("sell_cta_ranges_kernel launch");
     if (plan->n_slices > 0) {
         rc = check_cuda(cudaFuncSetAttribute(sell_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSellFillSmem),
                         "cudaFuncSetAttribute(sell_fill_kernel)");
@@ -668,7 +672,7 @@ int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full
                             const egnn_peer_window* win) {
     EGNN_REQUIRE(plan && dinv_full && iso_full && t_prev_local && out_local && coeffs_host, "null pointer");
     EGNN_REQUIRE(win || y_prev_full, "operand missing");
-    EGNN_REQUIRE(plan->vpart && plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr && plan->vslot, "SELL plan is not filled");
+    EGNN_REQUIRE(plan->vpart && plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr && plan->vslot && plan->cta_ptr, "SELL plan is not filled");
     EGNN_REQUIRE(order >= 1 && order <= k_max && k_max <= EGNN_MAX_ORDER, "bad order");
     EGNN_REQUIRE(n_scales >= 1 && n_scales <= EGNN_MAX_SCALES, "n_scales out of range");
     EGNN_REQUIRE(order == 1 || t_prev2_local, "T_{k-2} missing");

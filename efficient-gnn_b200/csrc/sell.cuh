@@ -163,6 +163,24 @@ sell_slice_kernel(int C, int lmax, const uint32_t* __restrict__ key_sorted,
     slice_sz[s] = (len + kSellGroup - 1) / kSellGroup * kSellGroup * kSellSliceRows;
 }
 
+// CTA g of the hot kernel handles slices [cta_ptr[g], cta_ptr[g+1]): an even
+// split of the padded entries on slice boundaries, computed once per plan (in
+// the hot kernel the two binary searches were ~30 dependent loads per CTA).
+__global__ void sell_cta_ranges_kernel(const int32_t* __restrict__ slice_off, int n_slices, int n_cta,
+                                       int32_t* __restrict__ cta_ptr) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_cta) return;
+    if (g == n_cta) { cta_ptr[g] = n_slices; return; }
+    const int64_t total = slice_off[n_slices];
+    const int64_t want = total * g / n_cta;
+    int lo = 0, hi = n_slices;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)slice_off[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    cta_ptr[g] = lo;
+}
+
 __global__ void sell_totals_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ rv_ptr,
                                    int n, int64_t* __restrict__ totals) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -327,36 +345,14 @@ template <int UNROLL, bool PEER>
 __global__ void __launch_bounds__(kSellThreads, 1)
 sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ slice_off,
                  const int32_t* __restrict__ blk_slice_ptr, const int32_t* __restrict__ vslot,
-                 int C, int CB, int n_slices, const float* y, int n,
+                 const int32_t* __restrict__ cta_ptr, int C, int CB, const float* y, int n,
                  float* __restrict__ vpart, const SellPeerWait pw) {
     extern __shared__ __align__(16) float ysm[];
     __shared__ int next_slice;
-    __shared__ int range[2];
     const int lane = threadIdx.x & 31;
     if (PEER) peer_consumer_wait(pw.local_flags, pw.epoch, pw.world, pw.rank, pw.error);
 
-    if (threadIdx.x == 0) {
-        // even split of the padded entries over the CTAs, on slice boundaries
-        const int64_t total = slice_off[n_slices];
-        const int64_t lo_e = total * blockIdx.x / gridDim.x;
-        const int64_t hi_e = total * (blockIdx.x + 1) / gridDim.x;
-        int bounds[2];
-        const int64_t want[2] = {lo_e, hi_e};
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            int lo = 0, hi = n_slices;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if ((int64_t)slice_off[mid] < want[t]) lo = mid + 1; else hi = mid;
-            }
-            bounds[t] = lo;
-        }
-        if (blockIdx.x == gridDim.x - 1) bounds[1] = n_slices;
-        range[0] = bounds[0];
-        range[1] = bounds[1];
-    }
-    __syncthreads();
-    const int s_begin = range[0], s_end = range[1];
+    const int s_begin = __ldg(cta_ptr + blockIdx.x), s_end = __ldg(cta_ptr + blockIdx.x + 1);
     if (s_begin >= s_end) return;
 
     for (int c = sell_block_of_slice(blk_slice_ptr, C, s_begin); c < C; ++c) {
@@ -382,14 +378,29 @@ sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ s
         if (threadIdx.x == 0) next_slice = sub_begin;
         __syncthreads();
 
-        while (true) {
-            int s = 0;
-            if (lane == 0) s = atomicAdd(&next_slice, 1);
-            s = __shfl_sync(0xffffffffu, s, 0);
-            if (s >= sub_end) break;
-            const int off = __ldg(slice_off + s);
-            const int groups = (__ldg(slice_off + s + 1) - off) / (kSellGroup * kSellSliceRows);
-            const int slot = __ldg(vslot + (size_t)s * kSellSliceRows + lane);
+        // slices are handed out dynamically; the NEXT slice's offsets and slot are
+        // fetched while the current one is processed (two dependent round trips
+        // per slice otherwise: counter -> offsets -> indices)
+        int s = 0;
+        if (lane == 0) s = atomicAdd(&next_slice, 1);
+        s = __shfl_sync(0xffffffffu, s, 0);
+        int off = 0, end = 0, slot = -1;
+        if (s < sub_end) {
+            off = __ldg(slice_off + s);
+            end = __ldg(slice_off + s + 1);
+            slot = __ldg(vslot + (size_t)s * kSellSliceRows + lane);
+        }
+        while (s < sub_end) {
+            int s_next = 0;
+            if (lane == 0) s_next = atomicAdd(&next_slice, 1);
+            s_next = __shfl_sync(0xffffffffu, s_next, 0);
+            int off_next = 0, end_next = 0, slot_next = -1;
+            if (s_next < sub_end) {
+                off_next = __ldg(slice_off + s_next);
+                end_next = __ldg(slice_off + s_next + 1);
+                slot_next = __ldg(vslot + (size_t)s_next * kSellSliceRows + lane);
+            }
+            const int groups = (end - off) / (kSellGroup * kSellSliceRows);
             const uint4* p = reinterpret_cast<const uint4*>(idx + off) + lane;
             float acc0 = 0.f, acc1 = 0.f;
             int g = 0;
@@ -405,6 +416,7 @@ sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ s
             }
             for (; g < groups; ++g) acc0 += sell_gather8(ysm, ld_stream_u32x4(p + (size_t)g * kSellSliceRows));
             if (slot >= 0) vpart[slot] = acc0 + acc1;
+            s = s_next; off = off_next; end = end_next; slot = slot_next;
         }
     }
 }
@@ -433,9 +445,17 @@ struct SellEpilogueParams {
 __device__ __forceinline__ void sell_epilogue_row(const SellEpilogueParams& p, int i) {
     // a hub row owns hundreds of virtual rows: add their partials in float64,
     // always in the same order (deterministic)
-    double accd = 0.0;
     const int e = __ldg(p.rv_ptr + i + 1);
-    for (int t = __ldg(p.rv_ptr + i); t < e; ++t) accd += (double)p.vpart[t];
+    int t = __ldg(p.rv_ptr + i);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;          // four interleaved chains, always combined the same way
+    for (; t + 4 <= e; t += 4) {
+        a0 += (double)p.vpart[t];
+        a1 += (double)p.vpart[t + 1];
+        a2 += (double)p.vpart[t + 2];
+        a3 += (double)p.vpart[t + 3];
+    }
+    for (; t < e; ++t) a0 += (double)p.vpart[t];
+    double accd = (a0 + a1) + (a2 + a3);
     for (int d = 0; d < p.delta.n; ++d)
         if (p.delta.row[d] == i + p.row0 && p.delta.col[d] != i + p.row0)
             accd += (double)p.delta.val[d] * (double)__ldg(p.y_prev + p.delta.col[d]);

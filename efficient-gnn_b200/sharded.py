@@ -325,18 +325,23 @@ class ShardedWavelet:
         fused_norm = normalize and not return_parts
 
         def slab():
-            return torch.zeros((rp, f), dtype=torch.float32, device=dev)
+            # rows beyond self.rows (short last shard) are exchanged but never read: no fill needed
+            return torch.empty((rp, f), dtype=torch.float32, device=dev)
 
-        out = torch.zeros((max(1, self.rows), n_scales, f), dtype=torch.float32, device=dev)
+        # order 1 writes every (row, scale, column) of out, so it is not cleared either
+        out = torch.empty((max(1, self.rows), n_scales, f), dtype=torch.float32, device=dev)
         orders = [x0]
         if k == 0:
             out[:self.rows] = torch.from_numpy(coeffs[:, 0]).to(dev).reshape(1, -1, 1) * x0.unsqueeze(1)
-        t_prev = slab()
-        t_prev[:self.rows] = x0
-        t_prev2 = None
-        full = torch.empty((self.world * rp, f), dtype=torch.float32, device=dev)
         use_plan = self.plan is not None and f == 1
         fused = use_plan and self.peer is not None
+        if fused or self.rows == rp:
+            t_prev = x0                       # no exchange of T_0 itself, or already slab-sized
+        else:
+            t_prev = slab()
+            t_prev[:self.rows] = x0
+        t_prev2 = None
+        full = None if fused else torch.empty((self.world * rp, f), dtype=torch.float32, device=dev)
         if fused:
             eng.peer_prescale_push(t_prev, self.dinv, self.rows, self.row_begin, self.peer.window)
             self.launches += 1

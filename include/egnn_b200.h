@@ -113,7 +113,7 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base,
  *   egnn_sell_prepare    counts (all passes but the last) in `workspace`,
  *                        SYNCHRONISES the stream and fills the size fields;
  *   (caller allocates slice_off[n_slices+1], blk_slice_ptr[n_blocks+1],
- *    idx[n_entries] (uint16, 256-byte aligned), rv_ptr[n+1], vslot[n_vrows],
+ *    idx[n_entries] (uint16, 256-byte aligned), rv_ptr[n+1], vslot[n_vrows], cta_ptr[n_cta+1],
  *    vpart[n_rowv] float32 scratch: row i's partial sums are
  *    vpart[rv_ptr[i] .. rv_ptr[i+1]), virtual row v writes vpart[vslot[v]])
  *   egnn_sell_fill       writes the index stream; `workspace` must be the
@@ -122,12 +122,14 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base,
 typedef struct egnn_sell_plan {
     int32_t n, n_blocks, col_block, lmax; /* n: rows laid out (a row shard or the whole graph) */
     int32_t n_cols, row0;                 /* columns = global nodes; global id of row 0        */
+    int32_t n_cta, reserved;              /* CTAs of the order kernel (set by prepare: SM count) */
     int64_t n_slices, n_vrows, n_entries, n_rowv;
     int32_t* slice_off;
     int32_t* blk_slice_ptr;
     uint16_t* idx;
     int32_t* rv_ptr;
     int32_t* vslot;
+    int32_t* cta_ptr;                     /* [n_cta + 1] slice range of every CTA (filled by egnn_sell_fill) */
     float* vpart;
 } egnn_sell_plan;
 
