@@ -9,6 +9,7 @@
 #include "peer.cuh"
 #include "prep.cuh"
 #include "sell.cuh"
+#include "wide.cuh"
 
 namespace egnn {
 
@@ -20,6 +21,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static int device_sm_count();
+constexpr int kWideMinF = 8;             // narrower signals keep the multi-row-per-warp kernel (cheb.cuh)
 
 static int pow2_ceil_log2(int64_t x) {
     int l = 0;
@@ -85,6 +89,38 @@ static int launch_order(const OrderParams& p, const OrderConfig& c, cudaStream_t
     else if (c.u == 1) launch_order_vu<1, 1>(p, has_vals, c.prescaled, grid, st);
     else launch_order_vu<1, 4>(p, has_vals, c.prescaled, grid, st);
     EGNN_LAUNCH_CHECK("cheb_order_kernel launch");
+    return EGNN_OK;
+}
+
+template <int VEC, int U, int NZ_LOG2>
+static void launch_wide_vun(const WideParams& p, dim3 grid, cudaStream_t st) {
+    if (p.vals) cheb_wide_kernel<VEC, U, NZ_LOG2, true><<<grid, kWideBlock, 0, st>>>(p);
+    else cheb_wide_kernel<VEC, U, NZ_LOG2, false><<<grid, kWideBlock, 0, st>>>(p);
+}
+
+// Wide kernel: persistent grid of kWideMinBlocks CTAs per SM per feature tile;
+// the lane layout (feature lanes x entry slots) is a compile-time variant.
+static int launch_wide(const WideParams& p, const OrderConfig& c, int sm_count, cudaStream_t st) {
+    dim3 grid((unsigned)(sm_count * kWideMinBlocks), (unsigned)c.grid_y, 1);
+    const int nz_log2 = 5 - c.fl_log2;
+    if (c.vec == 4) {
+        switch (nz_log2) {
+            case 0: launch_wide_vun<4, 1, 0>(p, grid, st); break;
+            case 1: launch_wide_vun<4, 1, 1>(p, grid, st); break;
+            case 2: launch_wide_vun<4, 1, 2>(p, grid, st); break;
+            case 3: launch_wide_vun<4, 1, 3>(p, grid, st); break;
+            default: launch_wide_vun<4, 1, 4>(p, grid, st); break;
+        }
+    } else if (c.u == 1) {
+        switch (nz_log2) {
+            case 0: launch_wide_vun<1, 1, 0>(p, grid, st); break;
+            case 1: launch_wide_vun<1, 1, 1>(p, grid, st); break;
+            default: launch_wide_vun<1, 1, 2>(p, grid, st); break;
+        }
+    } else {
+        launch_wide_vun<1, 4, 0>(p, grid, st);
+    }
+    EGNN_LAUNCH_CHECK("cheb_wide_kernel launch");
     return EGNN_OK;
 }
 
@@ -341,8 +377,49 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base, const floa
     return EGNN_OK;
 }
 
+static size_t row_order_cub_bytes(int64_t n) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int)n);
+    return b + 256;
+}
+
+size_t egnn_row_order_ws_bytes(int64_t n) {
+    if (n < 1) return 256;
+    return 3 * align_up(4 * (size_t)n, 256) + row_order_cub_bytes(n) + 256;
+}
+
+int egnn_row_order(const int32_t* rowptr, int64_t n, int32_t* order_out, void* workspace, size_t workspace_bytes,
+                   egnn_stream_t stream) {
+    EGNN_REQUIRE(rowptr && order_out, "null pointer");
+    EGNN_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return check_cuda(cudaMemsetAsync(order_out, 0, sizeof(int32_t), st), "memset n_hub");
+    const size_t need = egnn_row_order_ws_bytes(n);
+    if (!workspace || workspace_bytes < need) {
+        set_error("row-order workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return EGNN_ERR_WORKSPACE;
+    }
+    const size_t arr = align_up(4 * (size_t)n, 256);
+    char* ws = (char*)align_up((size_t)workspace, 256);
+    uint32_t* keys = (uint32_t*)ws;
+    uint32_t* keys_sorted = (uint32_t*)(ws + arr);
+    int32_t* ids = (int32_t*)(ws + 2 * arr);
+    void* cub_temp = ws + 3 * arr;
+    size_t cub_bytes = row_order_cub_bytes(n);
+    row_order_keys_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(rowptr, (int)n, keys, ids);
+    EGNN_LAUNCH_CHECK("row_order_keys_kernel launch");
+    int rc = check_cuda(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys, keys_sorted, ids, order_out, (int)n, 0,
+                                                        32, st), "sort rows by degree");
+    if (rc) return rc;
+    row_order_hubs_kernel<<<1, 32, 0, st>>>(keys_sorted, (int)n, order_out + n);
+    EGNN_LAUNCH_CHECK("row_order_hubs_kernel launch");
+    return EGNN_OK;
+}
+
 size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f) {
     // two T ping-pong slabs + two pre-scaled gather slabs (narrow F only)
+    // f <= 4: two T slabs + two pre-scaled slabs; 4 < f < 8: two T slabs; f >= 8: two pre-scaled slabs
     const size_t slab = align_up(sizeof(float) * (size_t)n * (size_t)f, 256);
     return slab * (f <= 4 ? 4 : 2) + 256;
 }
@@ -354,7 +431,7 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
                       const int32_t* delta_row_host, const int32_t* delta_col_host,
                       const float* delta_val_host, int32_t n_delta, void* workspace,
                       size_t workspace_bytes, egnn_stream_t stream, void* const* order_events_host,
-                      const egnn_sell_plan* sell_plan) {
+                      const egnn_sell_plan* sell_plan, const int32_t* row_order_or_null) {
     EGNN_REQUIRE(rowptr && dinv && iso && x0 && out && coeffs_host, "null pointer");
     EGNN_REQUIRE(nnz == 0 || colidx, "null colidx");
     EGNN_REQUIRE(n >= 0 && n < (int64_t(1) << 31) && nnz >= 0 && nnz < (int64_t(1) << 31), "n/nnz out of int32 range");
@@ -450,6 +527,49 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
             EGNN_LAUNCH_CHECK("sell_epilogue_kernel launch");
             t_prev2 = t_prev;
             t_prev = t_out;
+        }
+        return EGNN_OK;
+    }
+
+    if (f >= kWideMinF) {
+        WideParams wp{};
+        wp.delta = p.delta;
+        wp.rowptr = rowptr; wp.colidx = colidx; wp.vals = vals_or_null;
+        wp.perm = row_order_or_null; wp.n_hub = row_order_or_null ? row_order_or_null + n : nullptr;
+        wp.dinv = dinv; wp.iso = iso; wp.out = out; wp.n_rows = n; wp.row0 = 0; wp.F = f; wp.S = n_scales;
+        wp.a = op_scale; wp.b = op_shift; wp.fl_log2 = cfg.fl_log2;
+        float* yb[2] = {tbuf[0], tbuf[1]};                  // the two slabs hold dinv (.) T_k here
+        prescale_kernel<<<grid_for((int64_t)slab_elems, 256), 256, 0, st>>>(x0, dinv, yb[0], n, f, 0);
+        EGNN_LAUNCH_CHECK("prescale_kernel launch");
+        const bool fuse_norm_w = normalize_l1 && cfg.grid_y == 1;
+        const int sms = device_sm_count();
+        for (int order = 1; order <= k; ++order) {
+            const bool last = order == k;
+            wp.first = order == 1;
+            wp.normalize = last && fuse_norm_w;
+            wp.ysrc = yb[(order - 1) & 1];
+            wp.x0_own = order == 1 ? x0 : nullptr;
+            wp.y2_own = order == 1 ? nullptr : yb[order & 1];
+            wp.y_out = last ? nullptr : yb[order & 1];      // in place over dinv (.) T_{k-2} (own row only)
+            wp.tk_out = t_all_or_null ? t_all_or_null + (size_t)order * slab_elems : nullptr;
+            for (int s = 0; s < n_scales; ++s) {
+                wp.c_prev[s] = coeffs_host[s * (k + 1) + order - 1];
+                wp.c_k[s] = coeffs_host[s * (k + 1) + order];
+            }
+            if (order_events_host) {
+                rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1)], st), "event record");
+                if (rc) return rc;
+            }
+            rc = launch_wide(wp, cfg, sms, st);
+            if (rc) return rc;
+            if (order_events_host) {
+                rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1) + 1], st), "event record");
+                if (rc) return rc;
+            }
+        }
+        if (normalize_l1 && !fuse_norm_w) {
+            l1_normalize_kernel<<<grid_for(n * n_scales * 32, 256), 256, 0, st>>>(out, n * n_scales, f);
+            EGNN_LAUNCH_CHECK("l1_normalize_kernel launch");
         }
         return EGNN_OK;
     }

@@ -144,6 +144,23 @@ class CsrGraph:
                                             _cabi.ptr(colsum), _cabi.ptr(self._unsorted_flag), _stream()),
                         "egnn_graph_prep")
         self._sell = None          # lazily built SELL plan (False: not applicable)
+        self._row_order = None     # lazily built processing order of the wide kernel
+
+    # -- processing order for the wide (F >= 8) kernel ----------------------------
+    def row_order(self):
+        """``int32[n + 1]``: rows by descending stored-entry count, then the
+        number of leading rows a whole CTA sums (include/egnn_b200.h
+        ``egnn_row_order``).  Built once per graph on the device."""
+        if self._row_order is None:
+            lib = _cabi.load()
+            with torch.cuda.device(self.device):
+                order = torch.empty(self.n + 1, dtype=torch.int32, device=self.device)
+                ws_bytes = int(lib.egnn_row_order_ws_bytes(self.n))
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+                _cabi.check(lib.egnn_row_order(_cabi.ptr(self.rowptr), self.n, _cabi.ptr(order), _cabi.ptr(ws),
+                                               ws_bytes, _stream()), "egnn_row_order")
+            self._row_order = order
+        return self._row_order
 
     # -- SELL plan for the narrow (F = 1) path ---------------------------------
     SELL_MIN_NNZ = 1 << 22         # below this the CSR is L2-resident and launch-bound anyway

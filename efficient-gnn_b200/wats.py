@@ -35,6 +35,9 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+WIDE_MIN_F = 8       # signals at least this wide run on the wide-row kernel (csrc/wide.cuh)
+
+
 def heat_coefficients(k: int, s) -> np.ndarray:
     """``alpha[j, i] = exp(-s_j * i)`` (calibration/WATS.py:65), float64 on the
     host, rounded to float32 when handed to the kernel."""
@@ -72,6 +75,7 @@ def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_
     plan = None
     if f == 1 and k >= 1 and use_sell is not False:
         plan = graph.sell_plan(force=bool(use_sell))
+    row_order = graph.row_order() if (f >= WIDE_MIN_F and k >= 1) else None
     with torch.cuda.device(dev):
         out = torch.empty((n, n_scales, f), dtype=torch.float32, device=dev)
         t_all = torch.empty((k + 1, n, f), dtype=torch.float32, device=dev) if want_orders else None
@@ -87,7 +91,7 @@ def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_
             _cabi.host_array(C.c_int32, [int(v) for v in d_cols]),
             _cabi.host_array(C.c_float, [float(v) for v in d_vals]), len(d_rows),
             _cabi.ptr(ws), ws_bytes, _stream(), order_events,
-            None if plan is None else C.byref(plan)), "egnn_cheb_wavelet")
+            None if plan is None else C.byref(plan), _cabi.ptr(row_order)), "egnn_cheb_wavelet")
     return out, t_all
 
 

@@ -166,7 +166,9 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
  * 2(k-1)+1 are recorded on `stream` around order k's kernel (per-kernel
  * timing for the roofline report; no effect on results).
  * sell_plan_or_null: when given (f == 1, binary adjacency) the orders run on
- * the SELL plan; rowptr/colidx are then only used for the argument checks.   */
+ * the SELL plan; rowptr/colidx are then only used for the argument checks.
+ * row_order_or_null: the processing order from egnn_row_order (used for
+ * f >= 8: longest rows first, hub rows summed by a whole CTA); NULL = CSR order. */
 size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f);
 int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx,
                       const float* vals_or_null, const float* dinv,
@@ -178,7 +180,14 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx,
                       const float* delta_val_host, int32_t n_delta,
                       void* workspace, size_t workspace_bytes,
                       egnn_stream_t stream, void* const* order_events_host,
-                      const egnn_sell_plan* sell_plan_or_null);
+                      const egnn_sell_plan* sell_plan_or_null, const int32_t* row_order_or_null);
+
+/* Processing order of the wide-signal kernel (new in this build): rows by
+ * descending stored-entry count.  order_out: int32[n + 1] - the permutation,
+ * then the number of leading rows long enough to be summed by a whole CTA.   */
+size_t egnn_row_order_ws_bytes(int64_t n);
+int egnn_row_order(const int32_t* rowptr, int64_t n, int32_t* order_out,
+                   void* workspace, size_t workspace_bytes, egnn_stream_t stream);
 
 /* ---- row-sharded variant (1-D partition) -------------------------
  * One order on the rows [row_begin, row_end) this rank owns; new in this

@@ -1,9 +1,9 @@
 mkdir -p gpurun_out
 A="--workload arxiv --f 128 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e"
-R="--workload reddit --f 64 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+R="--workload physics --f 8415 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 python bench.py $A > gpurun_out/plain_arxiv.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:cheb_order -s 9 -c 3 -f -o gpurun_out/prof_wide_arxiv python bench.py $A > gpurun_out/ncu_arxiv.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:cheb_wide -s 9 -c 2 -f -o gpurun_out/prof_wide2_arxiv python bench.py $A > gpurun_out/ncu_arxiv.log 2>&1
 echo arxiv rc=$?
-python bench.py $R > gpurun_out/plain_reddit64.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:cheb_order -s 9 -c 1 -f -o gpurun_out/prof_wide_reddit64 python bench.py $R > gpurun_out/ncu_reddit64.log 2>&1
-echo reddit rc=$?
+python bench.py $R > gpurun_out/plain_physics.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:cheb_wide -s 10 -c 1 -f -o gpurun_out/prof_wide2_physics python bench.py $R > gpurun_out/ncu_physics.log 2>&1
+echo physics rc=$?

@@ -206,6 +206,30 @@ def test_edge_flip_deltas_match_rebuilt_graph():
     assert torch.equal(egnn.graph_wavelet_features(g, deltas=([], [], [])), egnn.graph_wavelet_features(g))
 
 
+def test_edge_flip_deltas_wide_signal():
+    """The same recompute with a 16-column signal (wide kernel: flips applied in its epilogue)."""
+    c = load_case("cora_loops")
+    n = c["n"]
+    dense = c["adj"].toarray()
+    target, others = 17, [3, 500, 1200, 2000, 2700]
+    nbrs = np.nonzero(dense[target])[0]
+    others[0] = int(nbrs[nbrs != target][0])
+    pert = dense.copy()
+    rows, cols, vals = [], [], []
+    for j in others:
+        v = -2 * dense[target, j] + 1
+        pert[target, j] += v
+        pert[j, target] += v
+        rows += [target, int(j)]
+        cols += [int(j), target]
+        vals += [float(v), float(v)]
+    x0 = np.random.default_rng(16).standard_normal((n, 16)).astype(np.float32)
+    g = egnn.CsrGraph.from_scipy(c["adj"])
+    res_d = egnn.graph_wavelet_features(g, X0=torch.from_numpy(x0), deltas=(rows, cols, vals), return_parts=True)
+    p = orc.wavelet_parts(sp.csr_matrix(pert.astype(np.float32)), x0=x0)
+    check_parts(res_d, p["T"], p["S"], p["H"], "delta wide")
+
+
 def test_isolating_flip_updates_iso():
     a = np.zeros((6, 6), np.float32)
     a[0, 1] = a[1, 0] = 1
@@ -249,6 +273,38 @@ def test_hub_row_accuracy():
     res = egnn.graph_wavelet_features(adj, k=3, X0=torch.from_numpy(x0), return_parts=True)
     p = orc.wavelet_parts(adj, k=3, x0=x0)
     check_parts(res, p["T"], p["S"], p["H"], "star")
+
+
+@pytest.mark.parametrize("f", [8, 16, 64, 130])
+def test_hub_row_accuracy_wide(f):
+    """The same star through the wide kernel: the 50k-entry row is summed by a
+    whole CTA (fixed-order shared-memory reduction), and twice gives equal bits."""
+    n = 50_001
+    hub = np.zeros(n - 1, dtype=np.int64)
+    leaves = np.arange(1, n, dtype=np.int64)
+    rows = np.concatenate([hub, leaves])
+    cols = np.concatenate([leaves, hub])
+    adj = sp.csr_matrix((np.ones(rows.size, np.float32), (rows, cols)), shape=(n, n))
+    x0 = np.random.default_rng(f).uniform(0.5, 1.5, (n, f)).astype(np.float32)
+    g = egnn.CsrGraph.from_scipy(adj)
+    assert int(g.row_order()[n].item()) == 1 and int(g.row_order()[0].item()) == 0
+    res = egnn.graph_wavelet_features(g, k=3, X0=torch.from_numpy(x0), return_parts=True)
+    p = orc.wavelet_parts(adj, k=3, x0=x0)
+    check_parts(res, p["T"], p["S"], p["H"], f"star wide {f}")
+    again = egnn.graph_wavelet_features(g, k=3, X0=torch.from_numpy(x0), return_parts=True)
+    for a, b in zip(res.orders, again.orders):
+        assert torch.equal(a, b)
+
+
+def test_row_order_is_a_degree_sorted_permutation():
+    rp, ci, n = synth.synth_csr("pubmed", self_loops=True)
+    g = egnn.CsrGraph(rp.cuda(), ci.cuda(), None, n)
+    order = g.row_order().cpu().numpy()
+    perm, n_hub = order[:n], int(order[n])
+    deg = np.diff(rp.numpy())
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    assert np.all(np.diff(deg[perm]) <= 0)
+    assert n_hub == int((deg >= 2048).sum())
 
 
 def test_errors_are_exceptions():
