@@ -92,36 +92,43 @@ static int launch_order(const OrderParams& p, const OrderConfig& c, cudaStream_t
     return EGNN_OK;
 }
 
-template <int VEC, int U, int NZ_LOG2>
-static void launch_wide_vun(const WideParams& p, dim3 grid, cudaStream_t st) {
-    if (p.vals) cheb_wide_kernel<VEC, U, NZ_LOG2, true><<<grid, kWideBlock, 0, st>>>(p);
-    else cheb_wide_kernel<VEC, U, NZ_LOG2, false><<<grid, kWideBlock, 0, st>>>(p);
+// Lane layout of the wide kernel for a padded row width ldy (multiple of 4):
+// FL feature lanes x NZ entry slots, tiles of FL * 4 columns in gridDim.y.
+struct RingConfig { int nz_log2, grid_y; };
+static RingConfig ring_config(int ldy) {
+    int fl_log2 = pow2_ceil_log2((ldy + 3) / 4);
+    if (fl_log2 > 5) fl_log2 = 5;
+    RingConfig c;
+    c.nz_log2 = 5 - fl_log2;
+    const int tile = (1 << fl_log2) * 4;
+    c.grid_y = (ldy + tile - 1) / tile;
+    return c;
 }
 
-// Wide kernel: persistent grid of kWideMinBlocks CTAs per SM per feature tile;
-// the lane layout (feature lanes x entry slots) is a compile-time variant.
-static int launch_wide(const WideParams& p, const OrderConfig& c, int sm_count, cudaStream_t st) {
-    dim3 grid((unsigned)(sm_count * kWideMinBlocks), (unsigned)c.grid_y, 1);
-    const int nz_log2 = 5 - c.fl_log2;
-    if (c.vec == 4) {
-        switch (nz_log2) {
-            case 0: launch_wide_vun<4, 1, 0>(p, grid, st); break;
-            case 1: launch_wide_vun<4, 1, 1>(p, grid, st); break;
-            case 2: launch_wide_vun<4, 1, 2>(p, grid, st); break;
-            case 3: launch_wide_vun<4, 1, 3>(p, grid, st); break;
-            default: launch_wide_vun<4, 1, 4>(p, grid, st); break;
-        }
-    } else if (c.u == 1) {
-        switch (nz_log2) {
-            case 0: launch_wide_vun<1, 1, 0>(p, grid, st); break;
-            case 1: launch_wide_vun<1, 1, 1>(p, grid, st); break;
-            default: launch_wide_vun<1, 1, 2>(p, grid, st); break;
-        }
+template <int NZ_LOG2>
+static int launch_wide_n(const WideParams& p, dim3 grid, cudaStream_t st) {
+    const bool aligned = (p.F % 4) == 0;
+    if (p.vals) {
+        if (aligned) cheb_wide_kernel<NZ_LOG2, true, true><<<grid, kWideBlock, 0, st>>>(p);
+        else cheb_wide_kernel<NZ_LOG2, true, false><<<grid, kWideBlock, 0, st>>>(p);
     } else {
-        launch_wide_vun<1, 4, 0>(p, grid, st);
+        if (aligned) cheb_wide_kernel<NZ_LOG2, false, true><<<grid, kWideBlock, 0, st>>>(p);
+        else cheb_wide_kernel<NZ_LOG2, false, false><<<grid, kWideBlock, 0, st>>>(p);
     }
     EGNN_LAUNCH_CHECK("cheb_wide_kernel launch");
     return EGNN_OK;
+}
+
+// Wide kernel: persistent grid of kWideMinBlocks CTAs per SM per feature tile.
+static int launch_wide(const WideParams& p, const RingConfig& c, int sm_count, cudaStream_t st) {
+    dim3 grid((unsigned)(sm_count * kWideMinBlocks), (unsigned)c.grid_y, 1);
+    switch (c.nz_log2) {
+        case 0: return launch_wide_n<0>(p, grid, st);
+        case 1: return launch_wide_n<1>(p, grid, st);
+        case 2: return launch_wide_n<2>(p, grid, st);
+        case 3: return launch_wide_n<3>(p, grid, st);
+        default: return launch_wide_n<4>(p, grid, st);
+    }
 }
 
 static int grid_for(int64_t work_items, int threads) {
@@ -420,7 +427,8 @@ int egnn_row_order(const int32_t* rowptr, int64_t n, int32_t* order_out, void* w
 size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f) {
     // two T ping-pong slabs + two pre-scaled gather slabs (narrow F only)
     // f <= 4: two T slabs + two pre-scaled slabs; 4 < f < 8: two T slabs; f >= 8: two pre-scaled slabs
-    const size_t slab = align_up(sizeof(float) * (size_t)n * (size_t)f, 256);
+    const size_t width = f >= kWideMinF ? (size_t)((f + 3) / 4 * 4) : (size_t)f;     // wide slabs have 16-byte rows
+    const size_t slab = align_up(sizeof(float) * (size_t)n * width, 256);
     return slab * (f <= 4 ? 4 : 2) + 256;
 }
 
@@ -532,16 +540,19 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
     }
 
     if (f >= kWideMinF) {
+        const int ldy = (f + 3) / 4 * 4;
+        const RingConfig rcfg = ring_config(ldy);
+        const size_t yslab = align_up(sizeof(float) * (size_t)n * (size_t)ldy, 256);
+        float* yb[2] = {(float*)ws, (float*)(ws + yslab)};       // the two slabs hold dinv (.) T_k, rows padded to 16 bytes
         WideParams wp{};
         wp.delta = p.delta;
         wp.rowptr = rowptr; wp.colidx = colidx; wp.vals = vals_or_null;
         wp.perm = row_order_or_null; wp.n_hub = row_order_or_null ? row_order_or_null + n : nullptr;
-        wp.dinv = dinv; wp.iso = iso; wp.out = out; wp.n_rows = n; wp.row0 = 0; wp.F = f; wp.S = n_scales;
-        wp.a = op_scale; wp.b = op_shift; wp.fl_log2 = cfg.fl_log2;
-        float* yb[2] = {tbuf[0], tbuf[1]};                  // the two slabs hold dinv (.) T_k here
-        prescale_kernel<<<grid_for((int64_t)slab_elems, 256), 256, 0, st>>>(x0, dinv, yb[0], n, f, 0);
-        EGNN_LAUNCH_CHECK("prescale_kernel launch");
-        const bool fuse_norm_w = normalize_l1 && cfg.grid_y == 1;
+        wp.dinv = dinv; wp.iso = iso; wp.out = out; wp.n_rows = n; wp.row0 = 0; wp.F = f; wp.ldy = ldy; wp.S = n_scales;
+        wp.a = op_scale; wp.b = op_shift;
+        prescale_pad_kernel<<<grid_for((int64_t)n * ldy, 256), 256, 0, st>>>(x0, dinv, yb[0], n, f, ldy, 0);
+        EGNN_LAUNCH_CHECK("prescale_pad_kernel launch");
+        const bool fuse_norm_w = normalize_l1 && rcfg.grid_y == 1;
         const int sms = device_sm_count();
         for (int order = 1; order <= k; ++order) {
             const bool last = order == k;
@@ -560,7 +571,7 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
                 rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1)], st), "event record");
                 if (rc) return rc;
             }
-            rc = launch_wide(wp, cfg, sms, st);
+            rc = launch_wide(wp, rcfg, sms, st);
             if (rc) return rc;
             if (order_events_host) {
                 rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1) + 1], st), "event record");
