@@ -905,18 +905,68 @@ int egnn_peer_error(const egnn_peer_window* win, int32_t* error_out, egnn_stream
     return EGNN_OK;
 }
 
-int egnn_peer_prescale_push(const float* x_local, const float* dinv_full, int64_t n_rows, int64_t row0,
+int egnn_peer_prescale_push(const float* x_local, const float* dinv_full, int64_t n_rows, int64_t row0, int32_t f,
                             const egnn_peer_window* win, egnn_stream_t stream) {
     EGNN_REQUIRE(dinv_full && win, "null pointer");
-    EGNN_REQUIRE(n_rows >= 0 && row0 >= 0 && (n_rows == 0 || x_local), "bad shape");
+    EGNN_REQUIRE(n_rows >= 0 && row0 >= 0 && f >= 1 && (n_rows == 0 || x_local), "bad shape");
     int rc = peer_check(win);
     if (rc) return rc;
-    EGNN_REQUIRE(win->f == 1 && row0 + n_rows <= (int64_t)win->world * win->rows_per, "window does not fit the rows");
+    EGNN_REQUIRE(win->f == (f >= kWideMinF ? (f + 3) / 4 * 4 : f) && row0 + n_rows <= (int64_t)win->world * win->rows_per,
+                 "window does not fit the signal");
     PeerPush pp{};
     fill_peer_push(pp, win, 0, true, true);
-    const int blocks = grid_for(n_rows > 0 ? n_rows : 1, 256);
-    peer_prescale_push_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x_local, dinv_full, n_rows, row0, pp);
+    const int blocks = grid_for(n_rows > 0 ? n_rows * win->f : 1, 256);
+    peer_prescale_push_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x_local, dinv_full, n_rows, row0, f, win->f, pp);
     EGNN_LAUNCH_CHECK("peer_prescale_push_kernel launch");
+    return EGNN_OK;
+}
+
+int egnn_wide_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_local, const float* vals_or_null,
+                            const int32_t* row_order_or_null, const float* dinv_full, const uint8_t* iso_full,
+                            const float* x0_local, float* t_out_local_or_null, float* out_local, int64_t n_global,
+                            int64_t row_begin, int64_t row_end, int32_t f, int32_t order, int32_t k_max,
+                            int32_t n_scales, const float* coeffs_host, float op_scale, float op_shift,
+                            int32_t normalize_l1, const egnn_peer_window* win, egnn_stream_t stream) {
+    EGNN_REQUIRE(rowptr_local && dinv_full && iso_full && out_local && coeffs_host && win, "null pointer");
+    EGNN_REQUIRE(row_begin >= 0 && row_end >= row_begin && row_end <= n_global, "bad row range");
+    EGNN_REQUIRE(f >= kWideMinF, "the wide sharded order serves f >= 8");
+    EGNN_REQUIRE(order >= 1 && order <= k_max && k_max <= EGNN_MAX_ORDER, "bad order");
+    EGNN_REQUIRE(n_scales >= 1 && n_scales <= EGNN_MAX_SCALES, "n_scales out of range");
+    EGNN_REQUIRE(order > 1 || x0_local || row_end == row_begin, "T_0 rows missing");
+    int rc = peer_check(win);
+    if (rc) return rc;
+    const int ldy = (f + 3) / 4 * 4;
+    EGNN_REQUIRE(win->f == ldy && (int64_t)win->world * win->rows_per >= n_global, "window does not fit the signal");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rows = row_end - row_begin;
+    const RingConfig rcfg = ring_config(ldy);
+    WideParams wp{};
+    wp.delta.n = 0;
+    wp.rowptr = rowptr_local; wp.colidx = colidx_local; wp.vals = vals_or_null;
+    wp.perm = row_order_or_null; wp.n_hub = row_order_or_null ? row_order_or_null + rows : nullptr;
+    wp.dinv = dinv_full; wp.iso = iso_full; wp.out = out_local; wp.n_rows = rows; wp.row0 = row_begin;
+    wp.F = f; wp.ldy = ldy; wp.S = n_scales; wp.a = op_scale; wp.b = op_shift;
+    const bool last = order == k_max;
+    const bool fuse_norm = normalize_l1 && rcfg.grid_y == 1;
+    wp.first = order == 1;
+    wp.normalize = last && fuse_norm;
+    wp.ysrc = peer_operand(win, win->rank, (order - 1) & 1);                  // full operand, global rows
+    wp.x0_own = order == 1 ? x0_local : nullptr;
+    float* own_next = peer_operand(win, win->rank, order & 1) + row_begin * (int64_t)ldy;
+    wp.y2_own = order == 1 ? nullptr : own_next;                              // dinv (.) T_{k-2} of the own rows
+    wp.y_out = (!last && win->world == 1) ? own_next : nullptr;               // single rank: plain store
+    wp.tk_out = t_out_local_or_null;
+    for (int s = 0; s < n_scales; ++s) {
+        wp.c_prev[s] = coeffs_host[s * (k_max + 1) + order - 1];
+        wp.c_k[s] = coeffs_host[s * (k_max + 1) + order];
+    }
+    fill_peer_push(wp.peer, win, order & 1, !last, false);
+    rc = launch_wide(wp, rcfg, device_sm_count(), st);
+    if (rc) return rc;
+    if (last && normalize_l1 && !fuse_norm && rows > 0) {
+        l1_normalize_kernel<<<grid_for(rows * n_scales * 32, 256), 256, 0, st>>>(out_local, rows * n_scales, f);
+        EGNN_LAUNCH_CHECK("l1_normalize_kernel launch");
+    }
     return EGNN_OK;
 }
 

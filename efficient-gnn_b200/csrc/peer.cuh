@@ -117,16 +117,20 @@ __device__ __forceinline__ void peer_producer_wait_first(const PeerPush& pp) {
     }
 }
 
-// y = dinv (.) x for the local rows, stored into every rank's operand buffer
-// (the order-1 operand of the narrow path).
+// y = dinv (.) x for the local rows, stored into every rank's operand buffer 0
+// (the order-1 operand).  x: [n_rows, f]; the window rows are ldy >= f wide and
+// the padding columns are written as zeros.
 __global__ void __launch_bounds__(256)
 peer_prescale_push_kernel(const float* __restrict__ x, const float* __restrict__ dinv, int64_t n_rows, int64_t row0,
-                          const __grid_constant__ PeerPush pp) {
+                          int32_t f, int32_t ldy, const __grid_constant__ PeerPush pp) {
     peer_producer_wait_first(pp);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows;
+    const int64_t total = n_rows * ldy;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = dinv[row0 + i] * x[i];
-        for (int p = 0; p < pp.world; ++p) pp.dst[p][row0 + i] = v;
+        const int64_t r = i / ldy;
+        const int c = (int)(i - r * ldy);
+        const float v = c < f ? dinv[row0 + r] * x[r * f + c] : 0.f;
+        for (int p = 0; p < pp.world; ++p) pp.dst[p][(row0 + r) * ldy + c] = v;
     }
     peer_producer_signal(pp);
 }

@@ -297,6 +297,8 @@ cheb_wide_kernel(const __grid_constant__ WideParams p) {
     if (n_hub > n_rows) n_hub = n_rows;
     const bool writer = nzl == 0 && col_ok;
     const float none[4] = {0.f, 0.f, 0.f, 0.f};
+    // row-sharded: the operand sits in this rank's exchange window and the other GPUs fill it
+    peer_consumer_wait(p.peer.local_flags, p.peer.epoch, p.peer.world, p.peer.rank, p.peer.error);
 
     // ---- phase A: hub rows, one CTA each, longest first ---------------------
     for (int h = blockIdx.x; h < n_hub; h += gridDim.x) {

@@ -31,7 +31,7 @@ import torch
 import torch.distributed as dist
 
 from . import _cabi
-from .wats import heat_coefficients
+from .wats import WIDE_MIN_F, heat_coefficients
 
 __all__ = ["RowPartition", "split_columns", "CudaEngine", "DistComm", "PeerExchange", "ShardedWavelet"]
 
@@ -147,9 +147,26 @@ class CudaEngine:
             coeffs.ctypes.data_as(C.c_void_p), float(op_scale), float(op_shift), 1 if normalize else 0, _stream(),
             None if window is None else C.byref(window)), "egnn_sell_order_sharded")
 
-    def peer_prescale_push(self, x_local, dinv, n_rows, row0, window):
-        _cabi.check(self.lib.egnn_peer_prescale_push(_cabi.ptr(x_local), _cabi.ptr(dinv), n_rows, row0,
+    def peer_prescale_push(self, x_local, dinv, n_rows, row0, f, window):
+        _cabi.check(self.lib.egnn_peer_prescale_push(_cabi.ptr(x_local), _cabi.ptr(dinv), n_rows, row0, f,
                                                      C.byref(window), _stream()), "egnn_peer_prescale_push")
+
+    # -- wide path with the exchange fused ---------------------------------------
+    def row_order(self, rowptr, n_rows):
+        order = torch.empty(n_rows + 1, dtype=torch.int32, device=self.device)
+        ws_bytes = int(self.lib.egnn_row_order_ws_bytes(n_rows))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        _cabi.check(self.lib.egnn_row_order(_cabi.ptr(rowptr), n_rows, _cabi.ptr(order), _cabi.ptr(ws), ws_bytes,
+                                            _stream()), "egnn_row_order")
+        return order
+
+    def wide_order(self, rowptr, colidx, row_order, dinv, iso, x0_local, t_out, out, n_global, row_begin, row_end, f,
+                   order, k_max, n_scales, coeffs, op_scale, op_shift, normalize, window):
+        _cabi.check(self.lib.egnn_wide_order_sharded(
+            _cabi.ptr(rowptr), _cabi.ptr(colidx), None, _cabi.ptr(row_order), _cabi.ptr(dinv), _cabi.ptr(iso),
+            _cabi.ptr(x0_local), _cabi.ptr(t_out), _cabi.ptr(out), n_global, row_begin, row_end, f, order, k_max,
+            n_scales, coeffs.ctypes.data_as(C.c_void_p), float(op_scale), float(op_shift), 1 if normalize else 0,
+            C.byref(window), _stream()), "egnn_wide_order_sharded")
 
     # -- stream plumbing ---------------------------------------------------------
     def side_stream(self):
@@ -279,9 +296,20 @@ class ShardedWavelet:
         # Fused exchange over peer memory for the narrow path: needs real peers
         # (one process per GPU, NCCL group) and the plan on every rank.
         self.peer = None
+        self._wide_peers = {}          # padded width -> PeerExchange of the wide path (built on first use)
+        self._row_order = None
+        self._group = group
         real_group = (comm is None and engine is None and self.world > 1 and dist.is_initialized()
                       and dist.get_backend(group) == "nccl")
-        if isinstance(peer_exchange, PeerExchange):       # reuse an existing window (same partition)
+        borrowed = None
+        if isinstance(peer_exchange, ShardedWavelet):     # reuse the windows of another instance (same partition)
+            borrowed, peer_exchange = peer_exchange, False
+            if borrowed.peer is not None:
+                if self.plan is None:
+                    raise _cabi.EgnnError("a shared exchange window needs the SELL plan on this rank")
+                self.peer = borrowed.peer
+            self._wide_peers = borrowed._wide_peers
+        elif isinstance(peer_exchange, PeerExchange):     # reuse an existing narrow-path window
             if self.plan is None:
                 raise _cabi.EgnnError("a shared exchange window needs the SELL plan on this rank")
             self.peer, peer_exchange = peer_exchange, False
@@ -294,7 +322,21 @@ class ShardedWavelet:
             dist.all_reduce(have, op=dist.ReduceOp.MIN, group=group)
             if int(have.item()) == 1:
                 self.peer = PeerExchange(self.part.rows_per, 1, group=group, device=self.device)
+        self.fused_wide = borrowed.fused_wide if borrowed is not None else bool(real_group and peer_exchange)
         self.launches = 0
+
+    def _wide_window(self, ldy: int):
+        """Exchange window for ``ldy``-wide operand rows (collective on first use)."""
+        if ldy not in self._wide_peers:
+            self._wide_peers[ldy] = PeerExchange(self.part.rows_per, ldy, group=self._group, device=self.device)
+        return self._wide_peers[ldy]
+
+    def exchange_error(self) -> int:
+        """Non-zero when any flag wait of the fused exchange timed out."""
+        err = 0 if self.peer is None else self.peer.error()
+        for px in self._wide_peers.values():
+            err |= px.error()
+        return err
 
     # -- collectives -------------------------------------------------------------
     def _allreduce(self, t):
@@ -335,6 +377,28 @@ class ShardedWavelet:
             out[:self.rows] = torch.from_numpy(coeffs[:, 0]).to(dev).reshape(1, -1, 1) * x0.unsqueeze(1)
         use_plan = self.plan is not None and f == 1
         fused = use_plan and self.peer is not None
+        fused_wide = self.fused_wide and f >= WIDE_MIN_F and k >= 1
+        if fused_wide:
+            # wide signal, exchange fused: operand rows live in the peers' windows (16-byte padded rows)
+            win = self._wide_window((f + 3) // 4 * 4).window
+            if self._row_order is None:
+                self._row_order = eng.row_order(self.rowptr, self.rows)
+            eng.peer_prescale_push(x0, self.dinv, self.rows, self.row_begin, f, win)
+            self.launches += 1
+            for order in range(1, k + 1):
+                t_out = torch.empty((self.rows, f), dtype=torch.float32, device=dev) if return_parts else None
+                eng.wide_order(self.rowptr, self.colidx, self._row_order, self.dinv, self.iso,
+                               x0 if order == 1 else None, t_out, out, self.n, self.row_begin, self.row_end, f, order,
+                               k, n_scales, coeffs, op_scale, op_shift, fused_norm, win)
+                self.launches += 1
+                if return_parts:
+                    orders.append(t_out)
+            out = out[:self.rows]
+            if return_parts:
+                comb = out
+                feats = comb / (comb.abs().sum(dim=2, keepdim=True) + 1e-8) if normalize else comb
+                return feats.reshape(self.rows, -1), orders, comb
+            return out.reshape(self.rows, -1)
         if fused or self.rows == rp:
             t_prev = x0                       # no exchange of T_0 itself, or already slab-sized
         else:
@@ -343,7 +407,7 @@ class ShardedWavelet:
         t_prev2 = None
         full = None if fused else torch.empty((self.world * rp, f), dtype=torch.float32, device=dev)
         if fused:
-            eng.peer_prescale_push(t_prev, self.dinv, self.rows, self.row_begin, self.peer.window)
+            eng.peer_prescale_push(t_prev, self.dinv, self.rows, self.row_begin, 1, self.peer.window)
             self.launches += 1
         elif use_plan:
             y_slabs = [slab(), slab()]
@@ -471,7 +535,7 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     dist.barrier()
     ms_per_step = float(ms.item())
-    peer_error = 0 if sw.peer is None else sw.peer.error()
+    peer_error = sw.exchange_error()
 
     # optional self-check: every rank also runs the single-GPU path on the whole graph
     check = None
@@ -500,7 +564,7 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
 
         def e2e_step():
             g = ShardedWavelet(rp_h.to(dev, non_blocking=True), ci_h.to(dev, non_blocking=True), n, device=dev,
-                               peer_exchange=sw.peer if sw.peer is not None else None)
+                               peer_exchange=sw)
             xx = None if x0_h is None else x0_h.to(dev, non_blocking=True)
             feats = g.features(k=k_max, s=scales, X0_local=xx)
             out_h[:sw.rows].copy_(feats, non_blocking=True)
@@ -541,10 +605,12 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
                        "f": f, "self_loops": True,
                        "parallelism": (f"{world} row shards, operand pushed into peer windows over NVLink by the "
                                        "epilogue kernel, flag wait in the next SpMV (no collective launch)"
-                                       if (sw.peer is not None and f == 1) else
+                                       if ((sw.peer is not None and f == 1) or (sw.fused_wide and f >= WIDE_MIN_F)) else
                                        f"{world} row shards, all_gather of the order operand per order (NCCL)"),
-                       "path": "sell-f1" if (sw.plan is not None and f == 1) else "csr-split-overlap",
-                       "exchange": "peer-window" if (sw.peer is not None and f == 1) else "nccl-allgather",
+                       "path": ("sell-f1" if (sw.plan is not None and f == 1) else
+                                "wide-fused" if (sw.fused_wide and f >= WIDE_MIN_F) else "csr-split-overlap"),
+                       "exchange": ("peer-window" if ((sw.peer is not None and f == 1) or
+                                                      (sw.fused_wide and f >= WIDE_MIN_F)) else "nccl-allgather"),
                        "cuda_graph": bool(use_graph),
                        "l2_policy": "per-rank CSR shard %.0f MB; no flush" % (4 * nnz / world / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",

@@ -264,11 +264,32 @@ int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full
 int egnn_prescale(const float* x, const float* dinv_full, float* y, int64_t n_rows,
                   int32_t f, int64_t row0, egnn_stream_t stream);
 
-/* The same product (F = 1) stored into operand buffer 0 of every rank's
- * window: first kernel of a fused-exchange step.  It first waits until every
- * peer has finished the previous step, then stores and signals.             */
+/* The same product stored into operand buffer 0 of every rank's window: first
+ * kernel of a fused-exchange step.  x_local is [n_rows, f]; the window rows are
+ * win->f wide (f for the narrow path, f rounded up to a multiple of 4 for
+ * f >= 8; padding columns are zeroed).  It first waits until every peer has
+ * finished the previous step, then stores and signals.                       */
 int egnn_peer_prescale_push(const float* x_local, const float* dinv_full, int64_t n_rows,
-                            int64_t row0, const egnn_peer_window* win, egnn_stream_t stream);
+                            int64_t row0, int32_t f, const egnn_peer_window* win,
+                            egnn_stream_t stream);
+
+/* One order of the wide (f >= 8) path on a row shard with the exchange fused
+ * (new in this build): the wide kernel runs on the rank's CSR rows
+ * [row_begin, row_end) (global column ids) against operand buffer (order-1)&1
+ * of its window - after waiting for the peers' flags - and its epilogue stores
+ * dinv (.) T_k of the own rows into buffer order&1 of EVERY rank's window, then
+ * signals.  win->f must be f rounded up to a multiple of 4.  x0_local: exact
+ * T_0 rows (order 1 only).  t_out_local_or_null: T_k rows [rows, f] when the
+ * caller wants every order.  row_order_or_null: egnn_row_order of the shard.  */
+int egnn_wide_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_local,
+                            const float* vals_or_null, const int32_t* row_order_or_null,
+                            const float* dinv_full, const uint8_t* iso_full,
+                            const float* x0_local, float* t_out_local_or_null, float* out_local,
+                            int64_t n_global, int64_t row_begin, int64_t row_end,
+                            int32_t f, int32_t order, int32_t k_max, int32_t n_scales,
+                            const float* coeffs_host, float op_scale, float op_shift,
+                            int32_t normalize_l1, const egnn_peer_window* win,
+                            egnn_stream_t stream);
 
 /* Degree pass of a row shard (scipy semantics as egnn_graph_prep).  phase 0:
  * row sums of the local rows, their diagonal entries into diag_full[row_begin..]

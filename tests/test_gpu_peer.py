@@ -24,7 +24,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, k, scales, steps, out_dir):
+def _worker(rank, world, port, k, scales, steps, out_dir, f=1):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -35,31 +35,38 @@ def _worker(rank, world, port, k, scales, steps, out_dir):
         part = sharded.RowPartition(n, world)
         rpl, cil = part.slice_csr(rp, ci, rank)
         sw = sharded.ShardedWavelet(rpl.to(dev), cil.to(dev), n, device=dev)
-        assert sw.plan is not None and sw.peer is not None, "fused exchange was not selected"
+        assert sw.plan is not None and sw.peer is not None and sw.fused_wide, "fused exchange was not selected"
+        x0 = None
+        if f > 1:
+            x0_full = np.random.default_rng(f).standard_normal((n, f)).astype(np.float32)
+            x0 = torch.from_numpy(x0_full[sw.row_begin:sw.row_end]).to(dev)
         outs = []
         for _ in range(steps):                       # consecutive steps reuse the two operand buffers
-            outs.append(sw.features(k=k, s=scales).cpu().numpy())
-        feats, orders, comb = sw.features(k=k, s=scales, return_parts=True)
-        assert sw.peer.error() == 0, "a flag wait timed out"
+            outs.append(sw.features(k=k, s=scales, X0_local=x0).cpu().numpy())
+        feats, orders, comb = sw.features(k=k, s=scales, X0_local=x0, return_parts=True)
+        assert sw.exchange_error() == 0, "a flag wait timed out"
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), b=sw.row_begin, e=sw.row_end,
                  fused=np.stack(outs), comb=comb.cpu().numpy(), **{f"t{i}": o.cpu().numpy() for i, o in enumerate(orders)})
         sw.peer.close()
+        for px in sw._wide_peers.values():
+            px.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,scales", [(3, 0.8), (4, [0.8, 1.6]), (1, 0.8)])
-def test_two_rank_fused_exchange_matches_oracle(tmp_path, k, scales):
+@pytest.mark.parametrize("k,scales,f", [(3, 0.8, 1), (4, [0.8, 1.6], 1), (1, 0.8, 1), (3, [0.8, 1.6], 16), (4, 0.8, 130)])
+def test_two_rank_fused_exchange_matches_oracle(tmp_path, k, scales, f):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (one process per GPU)")
     import torch.multiprocessing as mp
     world, steps = 2, 3
-    mp.spawn(_worker, args=(world, _free_port(), k, scales, steps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), k, scales, steps, str(tmp_path), f), nprocs=world, join=True)
     rp, ci, n = synth.synth_csr(SHAPE, self_loops=True)
     adj = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
-    p = orc.wavelet_parts(adj, k=k, s=scales)
+    x0_full = None if f == 1 else np.random.default_rng(f).standard_normal((n, f)).astype(np.float32)
+    p = orc.wavelet_parts(adj, k=k, s=scales, x0=x0_full)
     want_h = np.concatenate(p["H"], axis=1).astype(np.float32)
-    want_s = np.stack(p["S"], axis=1)                                   # [N, S, 1]
+    want_s = np.stack(p["S"], axis=1)                                   # [N, S, F]
     sure = np.concatenate([np.abs(sj) > 1e-4 * np.abs(sj).max() for sj in p["S"]], axis=1)
     for rank in range(world):
         z = np.load(tmp_path / f"rank{rank}.npz")
