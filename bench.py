@@ -53,6 +53,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="N>1: do not replay the step as a CUDA graph")
+    ap.add_argument("--no-sell", action="store_true", help="F=1: use the generic CSR kernel instead of the SELL plan")
+    ap.add_argument("--flips", type=int, default=0,
+                    help="UGCA mode (N=1): every step recomputes the features of the graph with this many symmetric "
+                         "edge flips around a random target node applied on top of the resident graph")
     ap.add_argument("--check", action="store_true", help="N>1: compare every rank's rows with the single-GPU path")
     return ap.parse_args()
 
@@ -233,8 +237,17 @@ def run_ours(args, rank, local_rank, world):
         x0 = torch.randn(n, f, device=dev, generator=torch.Generator(device=dev).manual_seed(sh.seed))
     work = float(nnz) * k_max * f
 
+    use_sell = False if args.no_sell else None
+    flips = None
+    if args.flips > 0:               # calib_fga.py:897-904: budget symmetric flips incident to one target node
+        gen = torch.Generator().manual_seed(7)
+        picks = torch.randint(0, n, (args.flips + 1,), generator=gen).tolist()
+        target, others = picks[0], [j for j in picks[1:] if j != picks[0]]
+        flips = ([target] * len(others) + others, others + [target] * len(others), [1.0] * (2 * len(others)))
+
     def step(events=None):
-        return egnn.graph_wavelet_features(graph, k=k_max, s=scales, X0=x0, _order_events=events)
+        return egnn.graph_wavelet_features(graph, k=k_max, s=scales, X0=x0, deltas=flips, _order_events=events,
+                                           _use_sell=use_sell)
 
     # per-order CUDA events (recorded by the library on the launching stream)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * k_max)] for _ in range(args.steps)]
@@ -279,7 +292,10 @@ def run_ours(args, rank, local_rank, world):
             traffic = json.load(open(tpath)).get(f"{args.workload}_f{f}_k{k_max}_s{n_scales}")
         except Exception:
             traffic = None
-    kernel_name = "sell_spmv_kernel" if (f == 1 and k_max >= 1 and graph.sell_plan() is not None) else "cheb_order_kernel"
+    if f == 1 and k_max >= 1 and not args.no_sell and graph.sell_plan() is not None:
+        kernel_name = "sell_spmv_kernel"
+    else:
+        kernel_name = "cheb_wide_kernel" if f >= 8 else "cheb_order_kernel"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": kernel_name, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sum(b_k) / k_max, "avg_launch_ms": avg_launch_ms,
@@ -299,7 +315,7 @@ def run_ours(args, rank, local_rank, world):
         def e2e_step():
             g = egnn.CsrGraph.from_host_csr(rp_h, ci_h, None, n, device=dev)
             xx = None if x0_h is None else x0_h.to(dev, non_blocking=True)
-            feats = egnn.graph_wavelet_features(g, k=k_max, s=scales, X0=xx)
+            feats = egnn.graph_wavelet_features(g, k=k_max, s=scales, X0=xx, _use_sell=use_sell)
             out_h.copy_(feats, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
@@ -326,13 +342,20 @@ def run_ours(args, rank, local_rank, world):
                                    f"nnz={adj.nnz}), same K/S/F; oracle port of calibration/WATS.py:39-74 "
                                    "(scipy, single-threaded like the reference), one run")}
 
-    launches_per_step = k_max + (1 if f <= 4 else 0) + (1 if f > 128 else 0)
+    # kernels of ours per step: SELL path = prescale + K x (SpMV + epilogue); wide path = padded prescale +
+    # K orders (+ L1 normalisation when the row spans several feature tiles); narrow generic = prescale + K
+    if kernel_name == "sell_spmv_kernel":
+        launches_per_step = 1 + 2 * k_max
+    elif f >= 8:
+        launches_per_step = 1 + k_max + (1 if (f + 3) // 4 * 4 > 128 else 0)
+    else:
+        launches_per_step = k_max + (1 if f <= 4 else 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}-shape", "n": n, "nnz": nnz, "k": k_max, "scales": n_scales, "f": f,
-                   "self_loops": True, "parallelism": "1 GPU", "l2_policy": (
+                   "self_loops": True, "parallelism": "1 GPU", "ugca_flips": int(args.flips), "l2_policy": (
                        "inputs larger than L2 (CSR %.0f MB vs 126 MB L2), no flush" % (4 * nnz / 1e6)
                        if 4 * nnz > 126e6 else "inputs fit in L2: latency-bound configuration, no flush")},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,

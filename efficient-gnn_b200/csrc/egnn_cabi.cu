@@ -330,6 +330,37 @@ int egnn_dense_to_csr_fill(const float* adj, int64_t n, int64_t ld, const int32_
     return EGNN_OK;
 }
 
+int egnn_degree_rows(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null, int64_t n,
+                     int64_t row_begin, int64_t row_end, float* rowsum, float* diag, double* colsum,
+                     int32_t* unsorted_flag_or_null, egnn_stream_t stream) {
+    EGNN_REQUIRE(rowptr && rowsum && diag && colsum, "null pointer");
+    EGNN_REQUIRE(n >= 0 && row_begin >= 0 && row_begin <= row_end && row_end <= n, "bad row range");
+    const int64_t rows = row_end - row_begin;
+    if (rows == 0) return EGNN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid_for(rows * 32, 256);
+    // rowptr values are absolute positions in colidx, so a row range is the same kernel on shifted row arrays
+    if (vals_or_null)
+        degree_kernel<true><<<g, 256, 0, st>>>(rowptr + row_begin, colidx, vals_or_null, rows, rowsum + row_begin,
+                                               diag + row_begin, colsum, unsorted_flag_or_null, row_begin);
+    else
+        degree_kernel<false><<<g, 256, 0, st>>>(rowptr + row_begin, colidx, nullptr, rows, rowsum + row_begin,
+                                                diag + row_begin, colsum, unsorted_flag_or_null, row_begin);
+    EGNN_LAUNCH_CHECK("degree_kernel launch");
+    return EGNN_OK;
+}
+
+int egnn_graph_prep_finish(const double* colsum, const float* diag, const float* rowsum, int64_t n, float* dinv,
+                           uint8_t* iso, float* x0_logdeg, float* w_out_or_null, egnn_stream_t stream) {
+    EGNN_REQUIRE(colsum && diag && rowsum && dinv && iso, "null pointer");
+    EGNN_REQUIRE(n >= 0, "bad shape");
+    if (n == 0) return EGNN_OK;
+    normaliser_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(colsum, diag, rowsum, n, dinv, iso,
+                                                                                    x0_logdeg, w_out_or_null);
+    EGNN_LAUNCH_CHECK("normaliser_kernel launch");
+    return EGNN_OK;
+}
+
 int egnn_graph_prep(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null, int64_t n,
                     float* dinv, uint8_t* iso, float* x0_logdeg, float* w_out_or_null,
                     float* rowsum_out, float* diag_ws, double* colsum_ws, int32_t* unsorted_flag_or_null,
@@ -344,18 +375,10 @@ int egnn_graph_prep(const int32_t* rowptr, const int32_t* colidx, const float* v
         rc = check_cuda(cudaMemsetAsync(unsorted_flag_or_null, 0, sizeof(int32_t), st), "memset flag");
         if (rc) return rc;
     }
-    const int g = grid_for(n * 32, 256);
-    if (vals_or_null)
-        degree_kernel<true><<<g, 256, 0, st>>>(rowptr, colidx, vals_or_null, n, rowsum_out, diag_ws, colsum_ws,
-                                               unsorted_flag_or_null, 0);
-    else
-        degree_kernel<false><<<g, 256, 0, st>>>(rowptr, colidx, nullptr, n, rowsum_out, diag_ws, colsum_ws,
-                                                unsorted_flag_or_null, 0);
-    EGNN_LAUNCH_CHECK("degree_kernel launch");
-    normaliser_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(colsum_ws, diag_ws, rowsum_out, n, dinv, iso,
-                                                                   x0_logdeg, w_out_or_null);
-    EGNN_LAUNCH_CHECK("normaliser_kernel launch");
-    return EGNN_OK;
+    rc = egnn_degree_rows(rowptr, colidx, vals_or_null, n, 0, n, rowsum_out, diag_ws, colsum_ws, unsorted_flag_or_null,
+                          stream);
+    if (rc) return rc;
+    return egnn_graph_prep_finish(colsum_ws, diag_ws, rowsum_out, n, dinv, iso, x0_logdeg, w_out_or_null, stream);
 }
 
 int egnn_patch_degrees(const float* w_base, const float* rowsum_base, const float* dinv_base,

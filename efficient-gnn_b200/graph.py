@@ -31,7 +31,8 @@ class CsrGraph:
     ``vals is None`` means a binary adjacency (every reference call site).
     """
 
-    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, vals: Optional[torch.Tensor], n: int):
+    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, vals: Optional[torch.Tensor], n: int,
+                 _prepare: bool = True):
         _cabi.require_device()
         if rowptr.dtype != torch.int32 or colidx.dtype != torch.int32:
             raise TypeError("rowptr/colidx must be int32")
@@ -47,7 +48,9 @@ class CsrGraph:
         if self.nnz >= 2 ** 31:
             raise ValueError("nnz must fit int32")
         self.device = rowptr.device
-        self._prepare()
+        self._alloc_vectors()
+        if _prepare:
+            self._prepare()
 
     # -- construction -------------------------------------------------------
     @classmethod
@@ -87,10 +90,63 @@ class CsrGraph:
         graph: asynchronous H2D copies on the current stream, then the degree
         pass.  This is the entry the host-buffer (end-to-end) timing uses."""
         _cabi.require_device()
-        rp = torch.as_tensor(rowptr).to(device, non_blocking=True)
-        ci = torch.as_tensor(colidx).to(device, non_blocking=True)
-        vv = None if vals is None else torch.as_tensor(vals).to(device, non_blocking=True)
-        return cls(rp, ci, vv, n)
+        rp_h, ci_h = torch.as_tensor(rowptr), torch.as_tensor(colidx)
+        vv_h = None if vals is None else torch.as_tensor(vals)
+        nnz = int(ci_h.numel())
+        pipelined = ci_h.is_pinned() and nnz >= cls.PIPELINE_MIN_NNZ and (vv_h is None or vv_h.is_pinned())
+        if not pipelined:
+            rp = rp_h.to(device, non_blocking=True)
+            ci = ci_h.to(device, non_blocking=True)
+            vv = None if vv_h is None else vv_h.to(device, non_blocking=True)
+            return cls(rp, ci, vv, n)
+        # Large pinned CSR: the entries are copied in row-aligned pieces on a side stream and the
+        # degree pass of each piece runs as soon as it has landed, so only the last piece's pass is
+        # left when the copy ends.
+        dev = torch.device(device)
+        lib = _cabi.load()
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            rp = rp_h.to(dev, non_blocking=True)
+            ci = torch.empty(nnz, dtype=torch.int32, device=dev)
+            vv = None if vv_h is None else torch.empty(nnz, dtype=torch.float32, device=dev)
+            g = cls(rp, ci, vv, n, _prepare=False)
+            g._colsum.zero_()
+            g._unsorted_flag.zero_()
+            pieces = max(2, min(16, nnz // cls.PIPELINE_PIECE_NNZ))
+            targets = torch.linspace(0, nnz, pieces + 1).to(torch.int64)
+            rows = torch.searchsorted(rp_h.to(torch.int64), targets, right=False).clamp_(max=n)
+            rows[0], rows[-1] = 0, n
+            rows = torch.unique_consecutive(rows).tolist()
+            copy = cls._copy_stream(dev)
+            copy.wait_stream(main)
+            for r0, r1 in zip(rows[:-1], rows[1:]):
+                lo, hi = int(rp_h[r0]), int(rp_h[r1])
+                with torch.cuda.stream(copy):
+                    ci[lo:hi].copy_(ci_h[lo:hi], non_blocking=True)
+                    if vv is not None:
+                        vv[lo:hi].copy_(vv_h[lo:hi], non_blocking=True)
+                    landed = torch.cuda.Event()
+                    landed.record(copy)
+                main.wait_event(landed)
+                _cabi.check(lib.egnn_degree_rows(_cabi.ptr(rp), _cabi.ptr(ci), _cabi.ptr(vv), n, r0, r1,
+                                                 _cabi.ptr(g.rowsum), _cabi.ptr(g._diag), _cabi.ptr(g._colsum),
+                                                 _cabi.ptr(g._unsorted_flag), _stream()), "egnn_degree_rows")
+            _cabi.check(lib.egnn_graph_prep_finish(_cabi.ptr(g._colsum), _cabi.ptr(g._diag), _cabi.ptr(g.rowsum), n,
+                                                   _cabi.ptr(g.dinv), _cabi.ptr(g.iso), _cabi.ptr(g.x0), _cabi.ptr(g.w),
+                                                   _stream()), "egnn_graph_prep_finish")
+            g._release_scratch()
+        return g
+
+    PIPELINE_MIN_NNZ = 1 << 24        # below this one copy + one pass is as fast
+    PIPELINE_PIECE_NNZ = 1 << 23      # ~32 MB of indices per piece
+    _copy_streams = {}
+
+    @classmethod
+    def _copy_stream(cls, dev):
+        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+        if key not in cls._copy_streams:
+            cls._copy_streams[key] = torch.cuda.Stream(device=dev)
+        return cls._copy_streams[key]
 
     @classmethod
     def from_scipy(cls, mat, device="cuda") -> "CsrGraph":
@@ -126,25 +182,33 @@ class CsrGraph:
         return cls(rowptr.to(torch.int32), (uniq % n).to(torch.int32), vals, n)
 
     # -- degree vectors -----------------------------------------------------
-    def _prepare(self):
+    def _alloc_vectors(self):
         n, dev = self.n, self.device
-        lib = _cabi.load()
         with torch.cuda.device(dev):
             self.dinv = torch.empty(n, dtype=torch.float32, device=dev)
             self.iso = torch.empty(n, dtype=torch.uint8, device=dev)
             self.x0 = torch.empty(n, dtype=torch.float32, device=dev)
             self.w = torch.empty(n, dtype=torch.float32, device=dev)
             self.rowsum = torch.empty(n, dtype=torch.float32, device=dev)
-            diag = torch.empty(n, dtype=torch.float32, device=dev)
-            colsum = torch.empty(n, dtype=torch.float64, device=dev)
+            self._diag = torch.empty(n, dtype=torch.float32, device=dev)
+            self._colsum = torch.empty(n, dtype=torch.float64, device=dev)
             self._unsorted_flag = torch.empty(1, dtype=torch.int32, device=dev)
-            _cabi.check(lib.egnn_graph_prep(_cabi.ptr(self.rowptr), _cabi.ptr(self.colidx), _cabi.ptr(self.vals), n,
-                                            _cabi.ptr(self.dinv), _cabi.ptr(self.iso), _cabi.ptr(self.x0),
-                                            _cabi.ptr(self.w), _cabi.ptr(self.rowsum), _cabi.ptr(diag),
-                                            _cabi.ptr(colsum), _cabi.ptr(self._unsorted_flag), _stream()),
-                        "egnn_graph_prep")
         self._sell = None          # lazily built SELL plan (False: not applicable)
+        self.narrow_calls = 0      # F = 1 passes run on this graph (the plan is built on the second)
         self._row_order = None     # lazily built processing order of the wide kernel
+
+    def _release_scratch(self):
+        self._diag = self._colsum = None
+
+    def _prepare(self):
+        lib = _cabi.load()
+        with torch.cuda.device(self.device):
+            _cabi.check(lib.egnn_graph_prep(_cabi.ptr(self.rowptr), _cabi.ptr(self.colidx), _cabi.ptr(self.vals), self.n,
+                                            _cabi.ptr(self.dinv), _cabi.ptr(self.iso), _cabi.ptr(self.x0),
+                                            _cabi.ptr(self.w), _cabi.ptr(self.rowsum), _cabi.ptr(self._diag),
+                                            _cabi.ptr(self._colsum), _cabi.ptr(self._unsorted_flag), _stream()),
+                        "egnn_graph_prep")
+        self._release_scratch()
 
     # -- processing order for the wide (F >= 8) kernel ----------------------------
     def row_order(self):
@@ -165,6 +229,9 @@ class CsrGraph:
     # -- SELL plan for the narrow (F = 1) path ---------------------------------
     SELL_MIN_NNZ = 1 << 22         # below this the CSR is L2-resident and launch-bound anyway
     SELL_MIN_SEGMENT = 16.0        # mean entries per (row, column block); padding grows below it
+
+    def has_sell_plan(self) -> bool:
+        return bool(self._sell)
 
     def sell_plan(self, force: bool = False):
         """The column-blocked sliced-ELL re-layout the F = 1 orders run on

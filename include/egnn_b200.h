@@ -89,6 +89,18 @@ int egnn_graph_prep(const int32_t* rowptr, const int32_t* colidx,
                     float* diag_ws, double* colsum_ws, int32_t* unsorted_flag_or_null,
                     egnn_stream_t stream);
 
+/* The same pass in pieces, for ingestion pipelined with the host->device copy
+ * of the CSR: the caller zero-fills colsum (and the flag) once, runs
+ * egnn_degree_rows on each row range as its entries arrive (it accumulates
+ * into colsum and writes rowsum/diag of the range), then egnn_graph_prep_finish. */
+int egnn_degree_rows(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null,
+                     int64_t n, int64_t row_begin, int64_t row_end,
+                     float* rowsum, float* diag, double* colsum,
+                     int32_t* unsorted_flag_or_null, egnn_stream_t stream);
+int egnn_graph_prep_finish(const double* colsum, const float* diag, const float* rowsum,
+                           int64_t n, float* dinv, uint8_t* iso, float* x0_logdeg,
+                           float* w_out_or_null, egnn_stream_t stream);
+
 /* UGCA recompute (the point where calib_attack/calib_fga.py:868,908,952 call
  * the calibrated surrogate on a perturbed adjacency): copies dinv/iso/x0 of
  * the base graph into the *_out vectors and re-derives the entries of every

@@ -296,6 +296,21 @@ def test_hub_row_accuracy_wide(f):
         assert torch.equal(a, b)
 
 
+def test_pipelined_host_ingestion_equals_one_shot(monkeypatch):
+    """Pinned host CSR copied in row-aligned pieces with the degree pass chasing the copy:
+    same vectors, bit for bit, as one copy + one pass."""
+    rp, ci, n = synth.synth_csr("physics", self_loops=True)
+    ref = egnn.CsrGraph(rp.cuda(), ci.cuda(), None, n)
+    monkeypatch.setattr(egnn.CsrGraph, "PIPELINE_MIN_NNZ", 0)
+    monkeypatch.setattr(egnn.CsrGraph, "PIPELINE_PIECE_NNZ", 40_000)
+    g = egnn.CsrGraph.from_host_csr(rp.pin_memory(), ci.pin_memory(), None, n)
+    torch.cuda.synchronize()
+    assert torch.equal(g.colidx, ref.colidx) and torch.equal(g.rowptr, ref.rowptr)
+    for name in ("dinv", "iso", "x0", "w", "rowsum"):
+        assert torch.equal(getattr(g, name), getattr(ref, name)), name
+    assert torch.equal(egnn.graph_wavelet_features(g), egnn.graph_wavelet_features(ref))
+
+
 def test_row_order_is_a_degree_sorted_permutation():
     rp, ci, n = synth.synth_csr("pubmed", self_loops=True)
     g = egnn.CsrGraph(rp.cuda(), ci.cuda(), None, n)
