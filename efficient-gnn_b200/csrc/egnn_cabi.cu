@@ -255,14 +255,14 @@ static int launch_sell_spmv(const egnn_sell_plan* pl, const float* y, int n_cols
                                                  (int)smem), "cudaFuncSetAttribute(sell_spmv_kernel)");
         if (rc) return rc;
         sell_spmv_kernel<kSellUnroll, true><<<sms, kSellThreads, smem, st>>>(
-            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->cta_ptr, pl->n_blocks, pl->col_block,
+            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->cta_ptr, pl->n_cta, pl->n_blocks, pl->col_block,
             peer_operand(win, win->rank, which), n_cols, pl->vpart, pw);
     } else {
         int rc = check_cuda(cudaFuncSetAttribute(sell_spmv_kernel<kSellUnroll, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)smem), "cudaFuncSetAttribute(sell_spmv_kernel)");
         if (rc) return rc;
         sell_spmv_kernel<kSellUnroll, false><<<sms, kSellThreads, smem, st>>>(
-            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->cta_ptr, pl->n_blocks, pl->col_block,
+            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->cta_ptr, pl->n_cta, pl->n_blocks, pl->col_block,
             y, n_cols, pl->vpart, pw);
     }
     EGNN_LAUNCH_CHECK("sell_spmv_kernel launch");
@@ -803,8 +803,8 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
     rc = check_cuda(cudaMemcpyAsync(plan->slice_off, w.slice_off, 4 * (plan->n_slices + 1), cudaMemcpyDeviceToDevice, st), "copy slice_off"); if (rc) return rc;
     rc = check_cuda(cudaMemcpyAsync(plan->blk_slice_ptr, w.bsp, 4 * (C + 1), cudaMemcpyDeviceToDevice, st), "copy blk_slice_ptr"); if (rc) return rc;
     rc = check_cuda(cudaMemcpyAsync(plan->rv_ptr, w.rv_ptr, 4 * (n + 1), cudaMemcpyDeviceToDevice, st), "copy rv_ptr"); if (rc) return rc;
-    sell_cta_ranges_kernel<<<(unsigned)ceil_div64(plan->n_cta + 1, 256), 256, 0, st>>>(w.slice_off, (int)plan->n_slices, plan->n_cta,
-                                                                                  plan->cta_ptr);
+    sell_cta_ranges_kernel<<<(unsigned)ceil_div64(plan->n_cta + 1, 256), 256, 0, st>>>(w.slice_off, w.bsp, C, (int)plan->n_slices,
+                                                                                  plan->n_cta, plan->cta_ptr);
     EGNN_LAUNCH_CHECK("sell_cta_ranges_kernel launch");
     if (plan->n_slices > 0) {
         rc = check_cuda(cudaFuncSetAttribute(sell_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSellFillSmem),

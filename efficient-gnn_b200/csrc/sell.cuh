@@ -166,11 +166,12 @@ sell_slice_kernel(int C, int lmax, const uint32_t* __restrict__ key_sorted,
 // CTA g of the hot kernel handles slices [cta_ptr[g], cta_ptr[g+1]): an even
 // split of the padded entries on slice boundaries, computed once per plan (in
 // the hot kernel the two binary searches were ~30 dependent loads per CTA).
-__global__ void sell_cta_ranges_kernel(const int32_t* __restrict__ slice_off, int n_slices, int n_cta,
-                                       int32_t* __restrict__ cta_ptr) {
+// cta_ptr[n_cta + 1 + g] = column block of that CTA's first slice.
+__global__ void sell_cta_ranges_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ blk_slice_ptr,
+                                       int C, int n_slices, int n_cta, int32_t* __restrict__ cta_ptr) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g > n_cta) return;
-    if (g == n_cta) { cta_ptr[g] = n_slices; return; }
+    if (g == n_cta) { cta_ptr[g] = n_slices; cta_ptr[n_cta + 1 + g] = C; return; }
     const int64_t total = slice_off[n_slices];
     const int64_t want = total * g / n_cta;
     int lo = 0, hi = n_slices;
@@ -179,6 +180,7 @@ __global__ void sell_cta_ranges_kernel(const int32_t* __restrict__ slice_off, in
         if ((int64_t)slice_off[mid] < want) lo = mid + 1; else hi = mid;
     }
     cta_ptr[g] = lo;
+    cta_ptr[n_cta + 1 + g] = sell_block_of_slice(blk_slice_ptr, C, lo);
 }
 
 __global__ void sell_totals_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ rv_ptr,
@@ -345,21 +347,49 @@ template <int UNROLL, bool PEER>
 __global__ void __launch_bounds__(kSellThreads, 1)
 sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ slice_off,
                  const int32_t* __restrict__ blk_slice_ptr, const int32_t* __restrict__ vslot,
-                 const int32_t* __restrict__ cta_ptr, int C, int CB, const float* y, int n,
+                 const int32_t* __restrict__ cta_ptr, int n_cta, int C, int CB, const float* y, int n,
                  float* __restrict__ vpart, const SellPeerWait pw) {
     extern __shared__ __align__(16) float ysm[];
     __shared__ int next_slice;
+    __shared__ int bsp[kSellMaxBlocks + 1];
     const int lane = threadIdx.x & 31;
-    if (PEER) peer_consumer_wait(pw.local_flags, pw.epoch, pw.world, pw.rank, pw.error);
+    const int wid = threadIdx.x >> 5;
+    constexpr int kWarps = kSellThreads / 32;
 
+    // everything that does not depend on the operand is requested first: this CTA's slice
+    // range and first column block (precomputed per plan), the block pointers, and - below -
+    // the index groups of every warp's first slice, which then fly during the flag wait
+    // (row-sharded) and the staging of the operand
     const int s_begin = __ldg(cta_ptr + blockIdx.x), s_end = __ldg(cta_ptr + blockIdx.x + 1);
-    if (s_begin >= s_end) return;
+    const int c_first = __ldg(cta_ptr + n_cta + 1 + blockIdx.x);
+    if (threadIdx.x <= C) bsp[threadIdx.x] = __ldg(blk_slice_ptr + threadIdx.x);
+    __syncthreads();
 
-    for (int c = sell_block_of_slice(blk_slice_ptr, C, s_begin); c < C; ++c) {
-        const int sub_begin = max(s_begin, blk_slice_ptr[c]);
-        const int sub_end = min(s_end, blk_slice_ptr[c + 1]);
+    bool waited = !PEER;
+    for (int c = c_first; c < C; ++c) {
+        const int sub_begin = max(s_begin, bsp[c]);
+        const int sub_end = min(s_end, bsp[c + 1]);
         if (sub_begin >= s_end) break;
         if (sub_begin >= sub_end) continue;
+
+        // this warp's first slice of the block is fixed (sub_begin + warp id); the rest are
+        // handed out dynamically from a shared counter
+        int s = sub_begin + wid;
+        int off = 0, end = 0, slot = -1;
+        if (s < sub_end) {
+            off = __ldg(slice_off + s);
+            end = __ldg(slice_off + s + 1);
+            slot = __ldg(vslot + (size_t)s * kSellSliceRows + lane);
+        }
+        // ask L2 for the head of that slice's index stream (one 128-byte line per lane, no registers held)
+        if (s < sub_end) {
+            const char* head = reinterpret_cast<const char*>(idx + off) + lane * 128;
+            if (head < reinterpret_cast<const char*>(idx + end)) asm volatile("prefetch.global.L2 [%0];" ::"l"(head));
+        }
+        if (!waited) {                                     // operand written by the other GPUs: wait for their flags
+            peer_consumer_wait(pw.local_flags, pw.epoch, pw.world, pw.rank, pw.error);
+            waited = true;
+        }
         __syncthreads();                                   // previous block's gathers are done
         // stage the column block of the operand in shared memory
         const int col0 = c * CB;
@@ -375,22 +405,11 @@ sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ s
             for (int t = threadIdx.x; t < cnt; t += kSellThreads) ysm[t] = PEER ? __ldcg(src + t) : __ldg(src + t);
         }
         for (int t = cnt + threadIdx.x; t < CB + kSellZeroSlots; t += kSellThreads) ysm[t] = 0.f;   // includes the zero slots
-        if (threadIdx.x == 0) next_slice = sub_begin;
+        if (threadIdx.x == 0) next_slice = sub_begin + kWarps;
         __syncthreads();
 
-        // slices are handed out dynamically; the NEXT slice's offsets and slot are
-        // fetched while the current one is processed (two dependent round trips
-        // per slice otherwise: counter -> offsets -> indices)
-        int s = 0;
-        if (lane == 0) s = atomicAdd(&next_slice, 1);
-        s = __shfl_sync(0xffffffffu, s, 0);
-        int off = 0, end = 0, slot = -1;
-        if (s < sub_end) {
-            off = __ldg(slice_off + s);
-            end = __ldg(slice_off + s + 1);
-            slot = __ldg(vslot + (size_t)s * kSellSliceRows + lane);
-        }
         while (s < sub_end) {
+            // the NEXT slice's offsets and slot are fetched while this one is summed
             int s_next = 0;
             if (lane == 0) s_next = atomicAdd(&next_slice, 1);
             s_next = __shfl_sync(0xffffffffu, s_next, 0);
@@ -419,6 +438,7 @@ sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ s
             s = s_next; off = off_next; end = end_next; slot = slot_next;
         }
     }
+    if (!waited) peer_consumer_wait(pw.local_flags, pw.epoch, pw.world, pw.rank, pw.error);   // CTA without slices
 }
 
 // ---- per-row epilogue -----------------------------------------------------------

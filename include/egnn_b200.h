@@ -125,7 +125,7 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base,
  *   egnn_sell_prepare    counts (all passes but the last) in `workspace`,
  *                        SYNCHRONISES the stream and fills the size fields;
  *   (caller allocates slice_off[n_slices+1], blk_slice_ptr[n_blocks+1],
- *    idx[n_entries] (uint16, 256-byte aligned), rv_ptr[n+1], vslot[n_vrows], cta_ptr[n_cta+1],
+ *    idx[n_entries] (uint16, 256-byte aligned), rv_ptr[n+1], vslot[n_vrows], cta_ptr[2*(n_cta+1)],
  *    vpart[n_rowv] float32 scratch: row i's partial sums are
  *    vpart[rv_ptr[i] .. rv_ptr[i+1]), virtual row v writes vpart[vslot[v]])
  *   egnn_sell_fill       writes the index stream; `workspace` must be the
@@ -141,7 +141,7 @@ typedef struct egnn_sell_plan {
     uint16_t* idx;
     int32_t* rv_ptr;
     int32_t* vslot;
-    int32_t* cta_ptr;                     /* [n_cta + 1] slice range of every CTA (filled by egnn_sell_fill) */
+    int32_t* cta_ptr;                     /* [2 * (n_cta + 1)] slice range, then first column block, of every CTA (egnn_sell_fill) */
     float* vpart;
 } egnn_sell_plan;
 
