@@ -37,7 +37,7 @@ import torch  # noqa: E402
 METRIC = "chebyshev_wavelet_nnz_k_f_per_s"
 UNIT = "nnz*K*F/s"
 DEFAULT_F = {"reddit": 1, "arxiv": 128, "physics": 1, "pubmed": 1, "cora": 1}
-CPU_RATE_GUESS = 6.4e6      # nnz*K*F/s of the reference path on one core
+CPU_RATE_GUESS = 2.0e7      # nnz*K*F/s of the oracle port on one host core (sizes the bounded CPU sample)
 
 
 def parse_args():
@@ -182,7 +182,7 @@ def run_reference(args, rank, world):
     f = args.f or DEFAULT_F[args.workload]
     scales = scale_list(args.scales)
     total = max(1, args.steps + args.warmup)
-    per_step = min(20.0, max(0.5, 150.0 / total))
+    per_step = min(10.0, max(0.5, 150.0 / total))
     adj, scale = cpu_sample_graph(args.workload, per_step, args.order, f, "cpu")
     for _ in range(args.warmup):
         time_oracle(adj, args.order, scales, f)
