@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="N>1: do not replay the step as a CUDA graph")
+    ap.add_argument("--entry", default="csr", choices=["csr", "dense"],
+                    help="e2e entry: pinned host CSR (default) or the reference's own boundary, a dense [N,N] float32 "
+                         "adjacency (calibration/WATS.py:99; small shapes only)")
     ap.add_argument("--no-sell", action="store_true", help="F=1: use the generic CSR kernel instead of the SELL plan")
     ap.add_argument("--flips", type=int, default=0,
                     help="UGCA mode (N=1): every step recomputes the features of the graph with this many symmetric "
@@ -312,8 +315,24 @@ def run_ours(args, rank, local_rank, world):
         h2d = rp_h.numel() * 4 + ci_h.numel() * 4 + (0 if x0_h is None else x0_h.numel() * 4)
         d2h = out_h.numel() * 4
 
+        entry = "CsrGraph.from_host_csr + graph_wavelet_features (pinned host CSR in, host features out)"
+        dense_h = None
+        if args.entry == "dense":
+            if 4 * n * n > 8e9:
+                raise SystemExit("--entry dense needs the [N,N] float32 adjacency to fit comfortably; use cora/pubmed/physics")
+            import scipy.sparse as sp
+            adj = sp.csr_matrix((np.ones(nnz, np.float32), graph.colidx.cpu().numpy(), graph.rowptr.cpu().numpy()),
+                                shape=(n, n))
+            dense_h = torch.from_numpy(adj.toarray()).pin_memory()
+            h2d = dense_h.numel() * 4 + (0 if x0_h is None else x0_h.numel() * 4)
+            entry = ("graph_wavelet_features(dense [N,N] float32 adjacency): pinned host dense in -> device "
+                     "dense->CSR kernels -> features -> host (the reference boundary, calibration/WATS.py:99-100)")
+
         def e2e_step():
-            g = egnn.CsrGraph.from_host_csr(rp_h, ci_h, None, n, device=dev)
+            if dense_h is not None:
+                g = egnn.CsrGraph.from_dense(dense_h.to(dev, non_blocking=True))
+            else:
+                g = egnn.CsrGraph.from_host_csr(rp_h, ci_h, None, n, device=dev)
             xx = None if x0_h is None else x0_h.to(dev, non_blocking=True)
             feats = egnn.graph_wavelet_features(g, k=k_max, s=scales, X0=xx, _use_sell=use_sell)
             out_h.copy_(feats, non_blocking=True)
@@ -329,8 +348,7 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
         e_dt = (time.perf_counter() - t0) / e_steps
         e2e = {"value": work / e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e_dt * 1e3, "steps": e_steps,
-               "entry": "CsrGraph.from_host_csr + graph_wavelet_features (pinned host CSR in, host features out)"}
+               "ms_per_step": e_dt * 1e3, "steps": e_steps, "entry": entry}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

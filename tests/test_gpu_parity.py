@@ -148,6 +148,16 @@ def test_feature_widths(f):
     np.testing.assert_allclose(fused.cpu().numpy(), np.concatenate(p["H"], axis=1), rtol=0, atol=3e-5)
 
 
+@pytest.mark.parametrize("f", [8, 18, 64, 131])
+def test_weighted_directed_graph_wide_signals(f):
+    """Non-symmetric weighted adjacency (in-degree normalisation, stored values) through the wide kernel."""
+    c = load_case("directed_weighted")
+    x0 = np.random.default_rng(100 + f).standard_normal((c["n"], f)).astype(np.float32)
+    res = egnn.graph_wavelet_features(c["adj"], k=3, s=[0.8, 0.4], X0=torch.from_numpy(x0), return_parts=True)
+    p = orc.wavelet_parts(c["adj"], k=3, s=[0.8, 0.4], x0=x0)
+    check_parts(res, p["T"], p["S"], p["H"], f"weighted F={f}")
+
+
 @pytest.mark.parametrize("lam", [1.5, 2.0, 2.7])
 def test_lambda_max(lam):
     c = load_case("cora_loops")
