@@ -45,6 +45,7 @@ SYMBOLS = {
     "egnn_peer_free": (C.c_int, [_P]),
     "egnn_peer_operand": (_P, [_P, _I32]),
     "egnn_peer_error": (C.c_int, [_P, _P, _P]),
+    "egnn_peer_wait_stats": (C.c_int, [_P, _P, _P, _I32, _P]),
     "egnn_peer_prescale_push": (C.c_int, [_P, _P, _I64, _I64, _I32, _P, _P]),
     "egnn_wide_order_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _I32,
                                           _P, _F32, _F32, _I32, _P, _P]),

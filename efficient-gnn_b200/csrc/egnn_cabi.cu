@@ -859,8 +859,13 @@ int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full
         fill_peer_push(ep.peer, win, order & 1, order < k_max, false);
         if (win->world == 1 && order < k_max) ep.y_out = peer_operand(win, 0, order & 1);   // single rank: plain store
     }
-    const unsigned blocks = (unsigned)ceil_div64(plan->n > 0 ? plan->n : 1, 256);
-    sell_epilogue_kernel<<<blocks, 256, 0, st>>>(ep);
+    if (fused) {                                    // one CTA per SM: one system fence per SM (sell.cuh)
+        int64_t blocks = ceil_div64(plan->n > 0 ? plan->n : 1, 1024);
+        if (blocks > plan->n_cta) blocks = plan->n_cta;
+        sell_epilogue_kernel<<<(unsigned)blocks, 1024, 0, st>>>(ep);
+    } else {
+        sell_epilogue_kernel<<<(unsigned)ceil_div64(plan->n > 0 ? plan->n : 1, 256), 256, 0, st>>>(ep);
+    }
     EGNN_LAUNCH_CHECK("sell_epilogue_kernel launch");
     return EGNN_OK;
 }
@@ -928,6 +933,27 @@ int egnn_peer_error(const egnn_peer_window* win, int32_t* error_out, egnn_stream
     return EGNN_OK;
 }
 
+int egnn_peer_wait_stats(const egnn_peer_window* win, uint64_t* total_ns, uint64_t* waits, int32_t reset,
+                         egnn_stream_t stream) {
+    EGNN_REQUIRE(win && total_ns && waits, "null pointer");
+    int rc = peer_check(win);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long v[2] = {0, 0};
+    char* stat = (char*)win->base[win->rank] + kPeerWaitNsOff;
+    rc = check_cuda(cudaMemcpyAsync(v, stat, 16, cudaMemcpyDeviceToHost, st), "copy wait stats");
+    if (rc) return rc;
+    rc = check_cuda(cudaStreamSynchronize(st), "sync");
+    if (rc) return rc;
+    if (reset) {
+        rc = check_cuda(cudaMemsetAsync(stat, 0, 16, st), "reset wait stats");
+        if (rc) return rc;
+    }
+    *total_ns = v[0];
+    *waits = v[1];
+    return EGNN_OK;
+}
+
 int egnn_peer_prescale_push(const float* x_local, const float* dinv_full, int64_t n_rows, int64_t row0, int32_t f,
                             const egnn_peer_window* win, egnn_stream_t stream) {
     EGNN_REQUIRE(dinv_full && win, "null pointer");
@@ -938,8 +964,10 @@ int egnn_peer_prescale_push(const float* x_local, const float* dinv_full, int64_
                  "window does not fit the signal");
     PeerPush pp{};
     fill_peer_push(pp, win, 0, true, true);
-    const int blocks = grid_for(n_rows > 0 ? n_rows * win->f : 1, 256);
-    peer_prescale_push_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x_local, dinv_full, n_rows, row0, f, win->f, pp);
+    int64_t blocks = ceil_div64(n_rows > 0 ? n_rows * win->f : 1, 1024);      // at most one CTA per SM: one system fence each
+    const int sms = device_sm_count();
+    if (blocks > sms) blocks = sms;
+    peer_prescale_push_kernel<<<(unsigned)blocks, 1024, 0, (cudaStream_t)stream>>>(x_local, dinv_full, n_rows, row0, f, win->f, pp);
     EGNN_LAUNCH_CHECK("peer_prescale_push_kernel launch");
     return EGNN_OK;
 }

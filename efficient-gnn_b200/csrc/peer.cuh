@@ -30,6 +30,8 @@ constexpr size_t kPeerFlagsOff = 0;
 constexpr size_t kPeerEpochOff = 256;
 constexpr size_t kPeerDoneOff = 260;
 constexpr size_t kPeerErrorOff = 264;
+constexpr size_t kPeerWaitNsOff = 512;     // uint64: total ns CTA 0 spent in flag waits (diagnostic)
+constexpr size_t kPeerWaitCntOff = 520;    // uint64: number of such waits
 constexpr size_t kPeerHeaderBytes = 4096;
 constexpr unsigned long long kPeerTimeoutNs = 8000000000ull;      // 8 s: a rank that never shows up
 
@@ -46,13 +48,16 @@ struct PeerPush {
     unsigned* error;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+// Flags are polled and raised with relaxed system-scope accesses; ordering comes from ONE
+// fence.sys after the poll loop / before the flag stores (an acquire load or release store per
+// peer would pay a fence each: measured ~4 us per peer on the 8-GPU box).
+__device__ __forceinline__ unsigned ld_relaxed_sys_u32(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
@@ -66,13 +71,20 @@ __device__ __forceinline__ void peer_wait_epoch(const unsigned* local_flags, int
     const unsigned long long t0 = global_timer_ns();
     for (int p = 0; p < world; ++p) {
         if (p == rank) continue;
-        while ((int)(ld_acquire_sys_u32(local_flags + p) - epoch) < 0) {
-            __nanosleep(64);
+        while ((int)(ld_relaxed_sys_u32(local_flags + p) - epoch) < 0) {
+            __nanosleep(32);
             if (global_timer_ns() - t0 > kPeerTimeoutNs) {
                 atomicExch(error, 1u);
                 return;
             }
         }
+    }
+    __threadfence_system();            // acquire: the peers' operand stores are visible past this point
+    if (blockIdx.x == 0 && blockIdx.y == 0) {          // diagnostic: how long the first CTA waited
+        unsigned long long* stat = reinterpret_cast<unsigned long long*>(
+            reinterpret_cast<char*>(const_cast<unsigned*>(local_flags)) - kPeerFlagsOff + kPeerWaitNsOff);
+        stat[0] += global_timer_ns() - t0;
+        stat[1] += 1ull;
     }
 }
 
@@ -88,22 +100,23 @@ __device__ __forceinline__ void peer_consumer_wait(const unsigned* local_flags, 
 
 // Tail of a producing kernel (all threads of every CTA call it after their
 // stores): the last CTA to arrive bumps the epoch and raises this rank's flag
-// in every window.  fence.sys before the counter makes each CTA's peer stores
-// visible system-wide before the flag can be seen.
+// in every window.  The CTA barrier orders every thread's peer stores before thread 0's
+// fence.sys (cumulative), which orders them before the counter; the last CTA fences once
+// more and raises the flags.
 __device__ __forceinline__ void peer_producer_signal(const PeerPush& pp) {
     if (pp.world <= 1) return;
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned total = gridDim.x * gridDim.y * gridDim.z;
         const unsigned prev = atomicAdd(pp.done_ctr, 1u);
         if (prev == total - 1) {
             *pp.done_ctr = 0u;                       // ready for the next producing launch
             const unsigned e = *pp.epoch + 1u;
             *pp.epoch = e;
-            __threadfence_system();
+            __threadfence_system();                  // release: every CTA's stores (seen through the counter) first
             for (int p = 0; p < pp.world; ++p)
-                if (p != pp.rank) st_release_sys_u32(pp.flag[p], e);
+                if (p != pp.rank) st_relaxed_sys_u32(pp.flag[p], e);
         }
     }
 }
@@ -120,7 +133,7 @@ __device__ __forceinline__ void peer_producer_wait_first(const PeerPush& pp) {
 // y = dinv (.) x for the local rows, stored into every rank's operand buffer 0
 // (the order-1 operand).  x: [n_rows, f]; the window rows are ldy >= f wide and
 // the padding columns are written as zeros.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 peer_prescale_push_kernel(const float* __restrict__ x, const float* __restrict__ dinv, int64_t n_rows, int64_t row0,
                           int32_t f, int32_t ldy, const __grid_constant__ PeerPush pp) {
     peer_producer_wait_first(pp);

@@ -500,10 +500,13 @@ __device__ __forceinline__ void sell_epilogue_row(const SellEpilogueParams& p, i
     }
 }
 
-__global__ void __launch_bounds__(256)
+// Launched with one row per thread (256-thread CTAs) on a single GPU; with the exchange
+// fused it runs as at most one 1024-thread CTA per SM striding over the rows, because every
+// CTA ends with a system-scope fence and those serialise per SM (8 CTAs per SM measured
+// ~8 us of fences per order, one CTA per SM ~3 us).
+__global__ void __launch_bounds__(1024)
 sell_epilogue_kernel(const __grid_constant__ SellEpilogueParams p) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < p.n) sell_epilogue_row(p, i);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) sell_epilogue_row(p, i);
     peer_producer_signal(p.peer);
 }
 

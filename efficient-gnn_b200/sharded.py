@@ -249,6 +249,14 @@ class PeerExchange:
             _cabi.check(self.lib.egnn_peer_error(C.byref(self.window), C.byref(out), _stream()), "egnn_peer_error")
         return out.value
 
+    def wait_stats(self, reset: bool = True):
+        """(total ns, count) of the flag waits seen by the first CTA (diagnostic)."""
+        ns, cnt = C.c_uint64(0), C.c_uint64(0)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.egnn_peer_wait_stats(C.byref(self.window), C.byref(ns), C.byref(cnt),
+                                                      1 if reset else 0, _stream()), "egnn_peer_wait_stats")
+        return ns.value, cnt.value
+
     def close(self):
         """Unmap the peers' windows and free this rank's (collective: nobody may
         still be storing into a window that is being freed)."""

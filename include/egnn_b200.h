@@ -252,6 +252,11 @@ void* egnn_peer_operand(const egnn_peer_window* win, int32_t which);
  * means a flag wait timed out (a peer never arrived).                         */
 int egnn_peer_error(const egnn_peer_window* win, int32_t* error_out, egnn_stream_t stream);
 
+/* Diagnostic: total nanoseconds the first CTA of the consuming kernels spent
+ * waiting for peer flags, and the number of waits (synchronises `stream`).   */
+int egnn_peer_wait_stats(const egnn_peer_window* win, uint64_t* total_ns, uint64_t* waits,
+                         int32_t reset, egnn_stream_t stream);
+
 /* One order of the narrow (F = 1) path on a row shard: SELL SpMV over the
  * rank's plan (plan->n rows starting at plan->row0, plan->n_cols columns)
  * against the exchanged full operand y_prev_full = dinv (.) T_{k-1} [n_cols],
