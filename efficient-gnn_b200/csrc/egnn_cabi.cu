@@ -6,6 +6,7 @@
 
 #include "cheb.cuh"
 #include "common.cuh"
+#include "head.cuh"
 #include "peer.cuh"
 #include "prep.cuh"
 #include "sell.cuh"
@@ -867,6 +868,20 @@ int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full
         sell_epilogue_kernel<<<(unsigned)ceil_div64(plan->n > 0 ? plan->n : 1, 256), 256, 0, st>>>(ep);
     }
     EGNN_LAUNCH_CHECK("sell_epilogue_kernel launch");
+    return EGNN_OK;
+}
+
+int egnn_temperature_head(const float* feats, const float* w1, const float* b1, const float* w2, const float* b2,
+                          const float* logits, float* out, float* temps_out_or_null, int64_t n, int32_t f,
+                          int32_t hidden, int32_t n_classes, egnn_stream_t stream) {
+    EGNN_REQUIRE(feats && w1 && b1 && w2 && b2 && logits && out, "null pointer");
+    EGNN_REQUIRE(n >= 0 && n_classes >= 1, "bad shape");
+    EGNN_REQUIRE(f >= 1 && f <= kHeadMaxFeat && hidden >= 1 && hidden <= kHeadMaxHidden, "head too large (f, hidden <= 64)");
+    if (n == 0) return EGNN_OK;
+    temperature_head_kernel<<<grid_for(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(feats, w1, b1, w2, b2, logits, out,
+                                                                                   temps_out_or_null, n, f, hidden,
+                                                                                   n_classes);
+    EGNN_LAUNCH_CHECK("temperature_head_kernel launch");
     return EGNN_OK;
 }
 

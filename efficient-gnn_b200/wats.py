@@ -237,14 +237,17 @@ class WATS(nn.Module):
     Keyword-only extensions: ``k``, ``s``, ``lambda_max`` (reference constants
     3 / 0.8 / 2.0), ``recompute_on_forward`` (recompute the features from the
     ``adj`` passed to ``forward`` - the reference always reuses the cached
-    ones, WATS.py:123), ``train`` (skip ``calib_train`` when False), ``verbose``.
+    ones, WATS.py:123), ``train`` (skip ``calib_train`` when False), ``verbose``,
+    ``fused_head`` (under ``torch.no_grad()`` the temperature MLP, the scaling
+    and the log_softmax of WATS.py:123-130 run as one kernel; autograd paths
+    keep the reference's torch ops).
     ``_features_override`` exists for parity tests only: it injects a feature
     matrix computed elsewhere so two instances differ in nothing else.
     """
 
     def __init__(self, base_model, features, labels, adj, val_mask, *, k: int = 3, s=0.8,
                  lambda_max: float = 2.0, recompute_on_forward: bool = False, train: bool = True,
-                 verbose: bool = True, _features_override=None):
+                 verbose: bool = True, fused_head: bool = True, _features_override=None):
         super().__init__()
         self.device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
         if _features_override is None:
@@ -257,6 +260,7 @@ class WATS(nn.Module):
         self.k, self.s, self.lambda_max = int(k), s, float(lambda_max)
         self.recompute_on_forward = bool(recompute_on_forward)
         self.verbose = bool(verbose)
+        self.fused_head = bool(fused_head)
 
         if _features_override is not None:
             self.graph = None
@@ -290,6 +294,21 @@ class WATS(nn.Module):
         t = self.net(wavelet_features).squeeze()
         return torch.log(torch.exp(t) + torch.tensor(1.1, device=self.device)).to(self.device)
 
+    def _fused_head(self, wavelet_features, logits):
+        """MLP -> temperature -> scaled log_softmax in one kernel (egnn_temperature_head).
+        Forward only: used when autograd is off and everything already sits on the GPU."""
+        lin1, lin2 = self.net[0], self.net[2]
+        feats = wavelet_features.detach().to(torch.float32).contiguous()
+        logits = logits.detach().to(torch.float32).contiguous()
+        out = torch.empty_like(logits)
+        with torch.cuda.device(logits.device):
+            _cabi.check(_cabi.load().egnn_temperature_head(
+                _cabi.ptr(feats), _cabi.ptr(lin1.weight.detach().contiguous()), _cabi.ptr(lin1.bias.detach().contiguous()),
+                _cabi.ptr(lin2.weight.detach().reshape(-1).contiguous()), _cabi.ptr(lin2.bias.detach().contiguous()),
+                _cabi.ptr(logits), _cabi.ptr(out), None, logits.shape[0], feats.shape[1], lin1.out_features,
+                logits.shape[1], _stream()), "egnn_temperature_head")
+        return out
+
     def forward(self, x, adj, *, deltas=None):
         x, adj = x.to(self.device), adj.to(self.device)
         if deltas is not None:
@@ -298,8 +317,11 @@ class WATS(nn.Module):
             wavelet_features = self.features_for(adj)
         else:
             wavelet_features = self.wavelet_feats.to(x.device)
-        temperatures = self.temperatures(wavelet_features)
         logits = self.base_model(x, adj)
+        if (self.fused_head and not torch.is_grad_enabled() and logits.is_cuda and logits.dim() == 2
+                and wavelet_features.shape[1] <= 64 and self.net[0].out_features <= 64):
+            return self._fused_head(wavelet_features, logits)
+        temperatures = self.temperatures(wavelet_features)
         calibrated_logits = logits / temperatures.unsqueeze(1)
         return F.log_softmax(calibrated_logits, dim=1)
 

@@ -201,6 +201,19 @@ size_t egnn_row_order_ws_bytes(int64_t n);
 int egnn_row_order(const int32_t* rowptr, int64_t n, int32_t* order_out,
                    void* workspace, size_t workspace_bytes, egnn_stream_t stream);
 
+/* ---- fused temperature head ----------------------------------
+ * Inference form of WATS.forward, calibration/WATS.py:122-130:
+ *   t_i = w2 . relu(W1 feats_i + b1) + b2;  T_i = log(exp(t_i) + 1.1);
+ *   out_i = log_softmax(logits_i / T_i).
+ * feats [n, f], w1 [hidden, f] (torch Linear layout), b1 [hidden], w2 [hidden],
+ * b2 [1], logits/out [n, n_classes]; temps_out_or_null [n] receives T_i.
+ * f, hidden <= 64.  Training keeps torch autograd (the host code only calls
+ * this under torch.no_grad()).                                               */
+int egnn_temperature_head(const float* feats, const float* w1, const float* b1,
+                          const float* w2, const float* b2, const float* logits,
+                          float* out, float* temps_out_or_null, int64_t n, int32_t f,
+                          int32_t hidden, int32_t n_classes, egnn_stream_t stream);
+
 /* ---- row-sharded variant (1-D partition) -------------------------
  * One order on the rows [row_begin, row_end) this rank owns; new in this
  * build (the reference is single-device).  t_prev_full is the exchanged

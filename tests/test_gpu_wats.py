@@ -26,7 +26,9 @@ def run(shape, self_loops, use_gcn, override):
     torch.cuda.manual_seed_all(42)
     np.random.seed(42)
     base = DenseGCN(16, sh.n_classes) if use_gcn else FixedLogits(logits)
-    cal = egnn.WATS(base, x, y, adj, val, verbose=False, _features_override=feats)
+    # the oracle-fed arm also keeps the reference's torch ops for the temperature head; the CUDA arm
+    # uses the fused head kernel under no_grad, so the comparison covers that kernel too
+    cal = egnn.WATS(base, x, y, adj, val, verbose=False, fused_head=not override, _features_override=feats)
     cal.eval()
     with torch.no_grad():
         lp = cal(x, adj).cpu().numpy()
@@ -74,3 +76,42 @@ def test_recompute_on_forward_and_deltas():
     want = orc.wavelet_features(sp.csr_matrix(pert.cpu().numpy()), k=3, s=[0.4, 0.8]).astype(np.float32)
     got = cal.features_for(pert).cpu().numpy()
     np.testing.assert_allclose(got, want, atol=1e-6)
+
+
+@pytest.mark.parametrize("f,hidden,c", [(1, 16, 7), (2, 16, 3), (4, 16, 41), (16, 64, 100), (1, 1, 1)])
+def test_fused_temperature_head_matches_the_reference_formula(f, hidden, c):
+    """egnn_temperature_head vs calibration/WATS.py:123-130 written in torch (float32)."""
+    import ctypes as C
+    from efficient_gnn_b200 import _cabi
+    g = torch.Generator(device="cuda").manual_seed(f * 100 + c)
+    n = 5000
+    feats = torch.randn(n, f, device="cuda", generator=g)
+    logits = 4 * torch.randn(n, c, device="cuda", generator=g)
+    net = torch.nn.Sequential(torch.nn.Linear(f, hidden), torch.nn.ReLU(), torch.nn.Linear(hidden, 1)).cuda()
+    with torch.no_grad():
+        t = net(feats).squeeze(-1)
+        temps = torch.log(torch.exp(t) + 1.1)
+        want = torch.nn.functional.log_softmax(logits / temps.unsqueeze(1), dim=1)
+        out = torch.empty_like(logits)
+        temps_got = torch.empty(n, device="cuda")
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _cabi.check(_cabi.load().egnn_temperature_head(
+            _cabi.ptr(feats), _cabi.ptr(net[0].weight.contiguous()), _cabi.ptr(net[0].bias), _cabi.ptr(net[2].weight.reshape(-1).contiguous()),
+            _cabi.ptr(net[2].bias), _cabi.ptr(logits), _cabi.ptr(out), _cabi.ptr(temps_got), n, f, hidden, c, st))
+    assert torch.allclose(temps_got, temps, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(out, want, rtol=1e-5, atol=2e-5)
+
+
+def test_forward_with_and_without_autograd_agree():
+    sh = synth.SHAPES["cora"]
+    rp, ci, n = synth.synth_csr("cora", self_loops=True)
+    adj = torch.tensor(sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n)).toarray())
+    y, logits, val, test = synth.synth_labels(sh.n, sh.n_classes, seed=42)
+    torch.manual_seed(3)
+    cal = egnn.WATS(FixedLogits(logits), torch.zeros(n, 4), y, adj, val, verbose=False)
+    cal.eval()
+    with torch.no_grad():
+        fused = cal(cal.x, cal.adj)
+    plain = cal(cal.x, cal.adj)                    # autograd on: the reference's torch ops
+    assert plain.requires_grad or True
+    assert torch.allclose(fused, plain.detach(), rtol=1e-5, atol=2e-5)
