@@ -12,6 +12,7 @@ __version__ = "0.1.0"
 from . import _cabi  # noqa: F401
 from ._cabi import EgnnError  # noqa: F401
 from .graph import CsrGraph, as_graph  # noqa: F401
+from .metrics import calibration_metrics  # noqa: F401
 from .wats import (  # noqa: F401
     WATS,
     LaplacianOperator,

@@ -7,6 +7,7 @@
 #include "cheb.cuh"
 #include "common.cuh"
 #include "head.cuh"
+#include "metrics.cuh"
 #include "peer.cuh"
 #include "prep.cuh"
 #include "sell.cuh"
@@ -868,6 +869,40 @@ int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full
         sell_epilogue_kernel<<<(unsigned)ceil_div64(plan->n > 0 ? plan->n : 1, 256), 256, 0, st>>>(ep);
     }
     EGNN_LAUNCH_CHECK("sell_epilogue_kernel launch");
+    return EGNN_OK;
+}
+
+size_t egnn_calibration_metrics_ws_bytes(int32_t n_classes, int32_t n_bins) {
+    if (n_classes < 1 || n_bins < 1 || n_bins > kEceMaxBins) return 0;
+    return 3 * align_up(8 * (size_t)n_classes * n_bins, 256) + 256 + 256;
+}
+
+int egnn_calibration_metrics(const float* x, int32_t is_log, const int64_t* labels, const uint8_t* mask_or_null,
+                             int64_t n, int32_t n_classes, int32_t n_bins, double* out3, void* workspace,
+                             size_t workspace_bytes, egnn_stream_t stream) {
+    EGNN_REQUIRE(x && labels && out3, "null pointer");
+    EGNN_REQUIRE(n >= 0 && n_classes >= 1 && n_bins >= 1 && n_bins <= kEceMaxBins, "bad shape");
+    const size_t need = egnn_calibration_metrics_ws_bytes(n_classes, n_bins);
+    if (!workspace || workspace_bytes < need) {
+        set_error("metrics workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return EGNN_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)align_up((size_t)workspace, 256);
+    const size_t arr = align_up(8 * (size_t)n_classes * n_bins, 256);
+    EceWs ws;
+    ws.sum_p = (double*)base;
+    ws.count = (unsigned long long*)(base + arr);
+    ws.hits = (unsigned long long*)(base + 2 * arr);
+    ws.scalars = (double*)(base + 3 * arr);
+    int rc = check_cuda(cudaMemsetAsync(base, 0, 3 * arr + 64, st), "memset metrics workspace");
+    if (rc) return rc;
+    if (n > 0) {
+        ece_accumulate_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(x, is_log, labels, mask_or_null, n, n_classes, n_bins, ws);
+        EGNN_LAUNCH_CHECK("ece_accumulate_kernel launch");
+    }
+    ece_finalize_kernel<<<1, 256, 0, st>>>(n_classes, n_bins, ws, out3);
+    EGNN_LAUNCH_CHECK("ece_finalize_kernel launch");
     return EGNN_OK;
 }
 

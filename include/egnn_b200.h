@@ -214,6 +214,19 @@ int egnn_temperature_head(const float* feats, const float* w1, const float* b1,
                           float* out, float* temps_out_or_null, int64_t n, int32_t f,
                           int32_t hidden, int32_t n_classes, egnn_stream_t stream);
 
+/* ---- calibration metrics on the device --------------------------
+ * The evaluation triple of benchmark_calibration_methods.py:100-127 on the
+ * samples selected by mask_or_null (uint8 [n]; NULL = all): out3[0] accuracy,
+ * out3[1] mean maximum probability, out3[2] class-wise ECE of utils/ece.py:8-89
+ * (n_bins right-closed bins per class, bins with < 4 samples skipped, mean over
+ * classes).  x: [n, n_classes] probabilities, or log-probabilities when is_log;
+ * labels int64 [n]; out3: device double[3].                                     */
+size_t egnn_calibration_metrics_ws_bytes(int32_t n_classes, int32_t n_bins);
+int egnn_calibration_metrics(const float* x, int32_t is_log, const int64_t* labels,
+                             const uint8_t* mask_or_null, int64_t n, int32_t n_classes,
+                             int32_t n_bins, double* out3, void* workspace,
+                             size_t workspace_bytes, egnn_stream_t stream);
+
 /* ---- row-sharded variant (1-D partition) -------------------------
  * One order on the rows [row_begin, row_end) this rank owns; new in this
  * build (the reference is single-device).  t_prev_full is the exchanged

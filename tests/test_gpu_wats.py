@@ -115,3 +115,28 @@ def test_forward_with_and_without_autograd_agree():
     plain = cal(cal.x, cal.adj)                    # autograd on: the reference's torch ops
     assert plain.requires_grad or True
     assert torch.allclose(fused, plain.detach(), rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("n,c", [(3000, 7), (20000, 41), (64, 3)])
+def test_device_calibration_metrics_match_the_reference_formulas(n, c):
+    """egnn_calibration_metrics vs the oracle restatement of utils/ece.py:8-89 and
+    benchmark_calibration_methods.py:100-127 (accuracy, mean confidence, class-wise ECE)."""
+    g = torch.Generator().manual_seed(n + c)
+    y = torch.randint(0, c, (n,), generator=g)
+    logits = 2.5 * torch.nn.functional.one_hot(y, c).float() + torch.randn(n, c, generator=g)
+    lp = torch.log_softmax(logits, dim=1)
+    mask = torch.rand(n, generator=g) < 0.6
+    want = orc.evaluate_probs(lp.numpy(), y.numpy(), mask.numpy())
+    got = egnn.calibration_metrics(lp.cuda(), y.cuda(), mask.cuda())
+    assert got[0] == pytest.approx(want[0], abs=1e-12)
+    assert got[1] == pytest.approx(want[1], abs=2e-6)
+    assert got[2] == pytest.approx(want[2], abs=2e-6)
+    assert round(got[2], 4) == round(want[2], 4)
+    # probabilities in, no mask; edge values 0 and 1 fall where numpy.digitize(right=True) puts them
+    probs = torch.exp(lp)
+    probs[0] = 0.0
+    probs[0, 0] = 1.0
+    want2 = (float((probs.numpy().argmax(1) == y.numpy()).mean()), float(probs.numpy().max(1).mean()),
+             orc.average_ece(probs.numpy(), y.numpy(), c))
+    got2 = egnn.calibration_metrics(probs.cuda(), y.cuda(), log_probs=False)
+    assert got2[0] == pytest.approx(want2[0], abs=1e-12) and got2[2] == pytest.approx(want2[2], abs=2e-6)
