@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--entry", default="csr", choices=["csr", "dense"],
                     help="e2e entry: pinned host CSR (default) or the reference's own boundary, a dense [N,N] float32 "
                          "adjacency (calibration/WATS.py:99; small shapes only)")
+    ap.add_argument("--replicas", action="store_true",
+                    help="N>1: UGCA replica mode - every rank holds the whole graph and recomputes the features of its "
+                         "own perturbation candidates (--flips, default 5); no exchange, weak scaling")
     ap.add_argument("--no-sell", action="store_true", help="F=1: use the generic CSR kernel instead of the SELL plan")
     ap.add_argument("--flips", type=int, default=0,
                     help="UGCA mode (N=1): every step recomputes the features of the graph with this many symmetric "
@@ -225,6 +228,8 @@ def run_ours(args, rank, local_rank, world):
     scales = scale_list(n_scales)
     sh = synth.SHAPES[args.workload]
 
+    if world > 1 and args.replicas:
+        return run_replicas(args, rank, local_rank, world)
     if world > 1:
         from efficient_gnn_b200 import sharded
         return sharded.bench_entry(args, rank, local_rank, world, METRIC, UNIT, algorithmic_bytes,
@@ -381,6 +386,68 @@ def run_ours(args, rank, local_rank, world):
         "clocks": sampler.summary(),
     }
     print(json.dumps(line), flush=True)
+
+
+def run_replicas(args, rank, local_rank, world):
+    """UGCA replica mode: candidates are independent, so each rank keeps the whole
+    graph resident and recomputes the features of its own candidates (edge flips around a target
+    node applied on top of the resident CSR / SELL plan).  No data-path collective."""
+    import torch.distributed as dist
+    import efficient_gnn_b200 as egnn
+    from efficient_gnn_b200 import synth
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    f = args.f or DEFAULT_F[args.workload]
+    k_max, n_scales = args.order, args.scales
+    scales = scale_list(n_scales)
+    rp, ci, n = synth.synth_csr(args.workload, self_loops=True, device=dev)
+    graph = egnn.CsrGraph(rp, ci, None, n)
+    nnz = graph.nnz
+    x0 = None if f == 1 else torch.randn(n, f, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    budget = args.flips or 5
+    gen = torch.Generator().manual_seed(1000 + rank)
+    cands = []
+    for _ in range(args.steps + max(3, args.warmup)):
+        picks = torch.randint(0, n, (budget + 1,), generator=gen).tolist()
+        t, others = picks[0], [j for j in picks[1:] if j != picks[0]]
+        cands.append(([t] * len(others) + others, others + [t] * len(others), [1.0] * (2 * len(others))))
+    it = iter(cands)
+    for _ in range(max(3, args.warmup)):
+        egnn.graph_wavelet_features(graph, k=k_max, s=scales, X0=x0, deltas=next(it))
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        egnn.graph_wavelet_features(graph, k=k_max, s=scales, X0=x0, deltas=next(it))
+    stop.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join()
+    ms = torch.tensor([start.elapsed_time(stop) / args.steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    ms_per_step = float(ms.item())
+    if rank == 0:
+        work = float(nnz) * k_max * f * world            # every rank finishes one candidate per step
+        line = {
+            "metric": METRIC, "value": work / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}-shape", "n": n, "nnz": nnz, "k": k_max, "scales": n_scales, "f": f,
+                       "self_loops": True, "ugca_flips": budget,
+                       "parallelism": f"{world} replicas: whole graph per GPU, one perturbation candidate per rank "
+                                      "per step, no exchange"},
+            "roofline": None, "cpu_baseline": None, "e2e": None,
+            "gpu_launches": int((1 + 2 * k_max + 1) * args.steps * world), "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 def main():
