@@ -841,9 +841,13 @@ int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full
     const bool fused = win && win->world > 1;
     if (plan->n == 0 && !fused) return EGNN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const float* operand = win ? peer_operand(win, win->rank, (order - 1) & 1) : y_prev_full;
-    if (plan->n_slices > 0 || fused) {
-        int rc = launch_sell_spmv(plan, operand, plan->n_cols, st, win, (order - 1) & 1);
+    // operand: the caller's full vector when given (also with a window: an operand every rank
+    // already holds, e.g. the default signal at order 1, needs no exchange and no wait), else
+    // buffer (order-1)&1 of the window
+    const bool from_window = win && !y_prev_full;
+    const float* operand = from_window ? peer_operand(win, win->rank, (order - 1) & 1) : y_prev_full;
+    if (plan->n_slices > 0 || (fused && from_window)) {
+        int rc = launch_sell_spmv(plan, operand, plan->n_cols, st, from_window ? win : nullptr, (order - 1) & 1);
         if (rc) return rc;
     }
     SellEpilogueParams ep{};

@@ -331,6 +331,16 @@ class ShardedWavelet:
             if int(have.item()) == 1:
                 self.peer = PeerExchange(self.part.rows_per, 1, group=group, device=self.device)
         self.fused_wide = borrowed.fused_wide if borrowed is not None else bool(real_group and peer_exchange)
+        # default signal X0 = log1p(degree): every rank keeps the whole pre-scaled vector (one
+        # all-gather at build time), so order 1 of the fused narrow path needs no exchange
+        self.y0_full = None
+        if self.peer is not None and self.world > 1:
+            rp_ = self.part.rows_per
+            pad = torch.zeros(rp_, dtype=torch.float32, device=self.device)
+            pad[:self.rows] = self.x0
+            full = torch.empty(self.world * rp_, dtype=torch.float32, device=self.device)
+            self._allgather(full, pad)
+            self.y0_full = (self.dinv * full[:self.n]).contiguous()
         self.launches = 0
 
     def _wide_window(self, ldy: int):
@@ -414,7 +424,8 @@ class ShardedWavelet:
             t_prev[:self.rows] = x0
         t_prev2 = None
         full = None if fused else torch.empty((self.world * rp, f), dtype=torch.float32, device=dev)
-        if fused:
+        y0_known = fused and X0_local is None and self.y0_full is not None
+        if fused and not y0_known:
             eng.peer_prescale_push(t_prev, self.dinv, self.rows, self.row_begin, 1, self.peer.window)
             self.launches += 1
         elif use_plan:
@@ -435,8 +446,9 @@ class ShardedWavelet:
                 t_out = t_prev2               # in place over T_{k-2} (read-then-write per element)
             if fused:
                 # operand already sits in every rank's window; SpMV waits on flags, epilogue pushes the next one
-                eng.sell_order(self.plan, None, self.dinv, self.iso, t_prev, t_prev2, t_out, None, out, order, k,
-                               n_scales, coeffs, op_scale, op_shift, fused_norm, window=self.peer.window)
+                eng.sell_order(self.plan, self.y0_full if (y0_known and order == 1) else None, self.dinv, self.iso,
+                               t_prev, t_prev2, t_out, None, out, order, k, n_scales, coeffs, op_scale, op_shift,
+                               fused_norm, window=self.peer.window)
                 self.launches += 2
             elif use_plan:
                 y_prev = y_slabs[(order - 1) & 1]

@@ -290,9 +290,11 @@ int egnn_peer_wait_stats(const egnn_peer_window* win, uint64_t* total_ns, uint64
  * dinv (.) T_k -> y_out_local (the slab the next exchange moves; or NULL),
  * scale accumulation into out_local [rows, n_scales].
  * With win_or_null given the exchange is fused: the SpMV waits for the peers'
- * flags and reads operand buffer (order-1)&1 of the window (y_prev_full is
- * ignored), the epilogue stores dinv (.) T_k into buffer order&1 of EVERY
- * rank's window and signals (y_out_local is ignored).                        */
+ * flags and reads operand buffer (order-1)&1 of the window - unless
+ * y_prev_full is also given, in which case that vector is the operand and
+ * nothing is waited for (an operand every rank already holds, e.g. the
+ * default signal at order 1) - and the epilogue stores dinv (.) T_k into
+ * buffer order&1 of EVERY rank's window and signals (y_out_local is ignored). */
 int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full,
                             const float* dinv_full, const uint8_t* iso_full,
                             const float* t_prev_local, const float* t_prev2_local,
