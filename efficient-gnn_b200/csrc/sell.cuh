@@ -201,9 +201,9 @@ __global__ void sell_totals_kernel(const int32_t* __restrict__ slice_off, const 
 // too).  One warp per slice: the 32 rows are placed one after the other by the
 // whole warp (coalesced reads of the CSR row, match_any for the per-bank
 // ordinals), staged in shared memory and written out with 16-byte stores.
-constexpr int kSellFillWarps = 4;
-constexpr int kSellLmaxCap = 256;          // positions per lane the staging buffer holds
-constexpr int kSellFillWarpHalves = kSellLmaxCap * kSellSliceRows + kSellLmaxCap + 64 + 16;   // stage + ovf + cnt + occ (uint16 units)
+constexpr int kSellFillWarps = 8;
+constexpr int kSellLmaxCap = 256;          // longest virtual row
+constexpr int kSellFillWarpHalves = kSellLmaxCap + 64 + 16;   // ovf + cnt + occ (uint16 units)
 constexpr size_t kSellFillSmem = (size_t)kSellFillWarps * kSellFillWarpHalves * sizeof(uint16_t);
 
 __global__ void __launch_bounds__(kSellFillWarps * 32)
@@ -219,8 +219,7 @@ sell_fill_kernel(const int32_t* __restrict__ colidx, int C, int CB, int lmax, in
     const int wid = threadIdx.x >> 5;
     const int s = blockIdx.x * kSellFillWarps + wid;
     if (s >= n_slices) return;
-    uint16_t* stage = fill_smem + (size_t)wid * kSellFillWarpHalves;
-    uint16_t* ovf = stage + kSellLmaxCap * kSellSliceRows;
+    uint16_t* ovf = fill_smem + (size_t)wid * kSellFillWarpHalves;
     int* cnt = reinterpret_cast<int*>(ovf + kSellLmaxCap);            // [32] entries seen per bank
     unsigned* occ = reinterpret_cast<unsigned*>(cnt + 32);            // [8] occupied positions
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -262,7 +261,10 @@ sell_fill_kernel(const int32_t* __restrict__ colidx, int C, int CB, int lmax, in
 #pragma unroll
             for (int t = 0; t < kBatches; ++t) cols_next[t] = (t * 32 + lane < l1) ? __ldg(colidx + s1 + t * 32 + lane) : -1;
         }
-        uint16_t* mine = stage + r * kSellGroup;                      // position j -> mine[(j >> 3) * 256 + (j & 7)]
+        // position j of row r lives at idx[off + ((j >> 3) * 32 + r) * 8 + (j & 7)]: written straight to
+        // global memory (2-byte stores that L2 merges); a shared-memory stage of the slice capped the
+        // kernel at 12 warps per SM and it was latency-bound
+        uint16_t* mine = idx + off + r * kSellGroup;
         cnt[lane] = 0;
         if (lane < kSellLmaxCap / 32) occ[lane] = 0u;
         __syncwarp();
@@ -305,10 +307,6 @@ sell_fill_kernel(const int32_t* __restrict__ colidx, int C, int CB, int lmax, in
         }
         __syncwarp();
     }
-    const int groups = lpad / kSellGroup;
-    const uint4* st4 = reinterpret_cast<const uint4*>(stage) + lane;
-    uint4* dst = reinterpret_cast<uint4*>(idx + off) + lane;
-    for (int g = 0; g < groups; ++g) dst[(size_t)g * kSellSliceRows] = st4[g * kSellSliceRows];
 }
 
 // ---- hot kernel ---------------------------------------------------------------
