@@ -461,10 +461,19 @@ struct SellEpilogueParams {
 };
 
 __device__ __forceinline__ void sell_epilogue_row(const SellEpilogueParams& p, int i) {
-    // a hub row owns hundreds of virtual rows: add their partials in float64,
-    // always in the same order (deterministic)
+    // everything that does not depend on the partial sums is requested first, so the row pays
+    // two dependent round trips (row pointers -> partials) instead of three
     const int e = __ldg(p.rv_ptr + i + 1);
     int t = __ldg(p.rv_ptr + i);
+    const float di = __ldg(p.dinv + p.row0 + i);
+    const float theta = fmaf(p.a, 1.f - (float)__ldg(p.iso + p.row0 + i), p.b);
+    float xprev = 0.f;
+    if (theta != 0.f || p.first) xprev = p.tprev[i];
+    const float t2 = p.first ? 0.f : p.tprev2[i];
+    float prev_out = 0.f;
+    if (!p.first && p.S == 1) prev_out = p.out[i];
+    // a hub row owns hundreds of virtual rows: add their partials in float64,
+    // always in the same order (deterministic)
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;          // four interleaved chains, always combined the same way
     for (; t + 4 <= e; t += 4) {
         a0 += (double)p.vpart[t];
@@ -478,12 +487,8 @@ __device__ __forceinline__ void sell_epilogue_row(const SellEpilogueParams& p, i
         if (p.delta.row[d] == i + p.row0 && p.delta.col[d] != i + p.row0)
             accd += (double)p.delta.val[d] * (double)__ldg(p.y_prev + p.delta.col[d]);
     const float acc = (float)accd;
-    const float di = __ldg(p.dinv + p.row0 + i);
-    const float theta = fmaf(p.a, 1.f - (float)__ldg(p.iso + p.row0 + i), p.b);
-    float xprev = 0.f;
-    if (theta != 0.f || p.first) xprev = p.tprev[i];
     const float lap = fmaf(theta, xprev, -p.a * di * acc);
-    const float tk = p.first ? lap : fmaf(2.f, lap, -p.tprev2[i]);
+    const float tk = p.first ? lap : fmaf(2.f, lap, -t2);
     if (p.tk) p.tk[i] = tk;
     if (p.y_out) p.y_out[i] = di * tk;
     if (p.peer.world > 1 && p.peer.has_data) {
@@ -492,7 +497,7 @@ __device__ __forceinline__ void sell_epilogue_row(const SellEpilogueParams& p, i
     }
     for (int s = 0; s < p.S; ++s) {
         float o = p.first ? fmaf(p.c_k[s], tk, p.c_prev[s] * xprev)
-                          : fmaf(p.c_k[s], tk, p.out[(size_t)i * p.S + s]);
+                          : fmaf(p.c_k[s], tk, p.S == 1 ? prev_out : p.out[(size_t)i * p.S + s]);
         if (p.normalize) o = o / (fabsf(o) + 1e-8f);
         p.out[(size_t)i * p.S + s] = o;
     }

@@ -332,6 +332,25 @@ def test_row_order_is_a_degree_sorted_permutation():
     assert n_hub == int((deg >= 2048).sum())
 
 
+def test_integration_stub_from_the_docs_runs():
+    """The ctypes stub printed in INTEGRATION.md (what a reference maintainer would add) is
+    executed as written against the built library and must reproduce the reference features."""
+    import os
+    import re
+    from efficient_gnn_b200 import _cabi
+    from helpers import ROOT
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n# calibration/_egnn\.py\n(.*?)```", text, re.S).group(1)
+    block = block.replace('C.CDLL("libegnn_b200.so")', f'C.CDLL({_cabi.LIB_PATH!r})')
+    ns = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    c = load_case("cora_loops")
+    dense = torch.tensor(c["adj"].toarray(), dtype=torch.float32, device="cuda")
+    got = ns["graph_wavelet_features"](dense, k=3, s=0.8).cpu().numpy()
+    sure = np.abs(c["S"]) > 1e-4 * np.abs(c["S"]).max()
+    np.testing.assert_allclose(got[sure], c["H"].astype(np.float32)[sure], rtol=0, atol=1e-6)
+
+
 def test_errors_are_exceptions():
     c = load_case("kat_path")
     g = egnn.CsrGraph.from_scipy(c["adj"])
