@@ -11,7 +11,7 @@
 //  * a warp owns one row x one feature tile (<= 128 columns: 32 lanes x float4,
 //    or NZ entries side by side when the tile is narrower); the row's indices
 //    are fetched 32 at a time with one coalesced load and broadcast by shuffle,
-//    8 row gathers are in flight per lane, full groups run branch-free, and the
+//    4 row gathers are in flight per lane (32 warps per SM), full groups run branch-free, and the
 //    NEXT row's pointers, first index batch and own-row operand are requested
 //    while this row is summed;
 //  * rows are dealt out cyclically from the degree-descending order
@@ -34,8 +34,17 @@ namespace egnn {
 
 constexpr int kWideBlock = 256;
 constexpr int kWideWarps = kWideBlock / 32;
-constexpr int kWideUnroll = 8;           // row gathers in flight per lane
-constexpr int kWideMinBlocks = 3;        // CTAs per SM the register budget is sized for
+// Measured on arxiv F=128 / Reddit F=64 / Physics F=8415 (ms per order): unroll 8 x 3 CTAs/SM
+// 0.35 / 2.81 / 3.15; 4 x 4: 0.285 / 2.14 / 2.73; 6 x 3: 0.29 / 2.50 / 2.75; 8 x 2: 0.30 / 2.27 /
+// 3.26; 4 x 5 and 2 x 6..8 (spilling): worse on arxiv.  More resident warps beat deeper unrolling.
+#ifndef EGNN_WIDE_UNROLL
+#define EGNN_WIDE_UNROLL 4
+#endif
+#ifndef EGNN_WIDE_BLOCKS
+#define EGNN_WIDE_BLOCKS 4
+#endif
+constexpr int kWideUnroll = EGNN_WIDE_UNROLL;      // row gathers in flight per lane
+constexpr int kWideMinBlocks = EGNN_WIDE_BLOCKS;   // CTAs per SM the register budget is sized for
 constexpr int kHubDegree = 2048;         // rows at least this long are summed by a whole CTA
 
 struct WideParams {
