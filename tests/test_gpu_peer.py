@@ -37,8 +37,8 @@ def _worker(rank, world, port, k, scales, steps, out_dir, f=1):
         sw = sharded.ShardedWavelet(rpl.to(dev), cil.to(dev), n, device=dev)
         assert sw.plan is not None and sw.peer is not None and sw.fused_wide, "fused exchange was not selected"
         x0 = None
-        if f > 1:
-            x0_full = np.random.default_rng(f).standard_normal((n, f)).astype(np.float32)
+        if f != 1:                                   # f == -1: a custom one-column signal (order-1 operand is exchanged too)
+            x0_full = np.random.default_rng(abs(f)).standard_normal((n, abs(f))).astype(np.float32)
             x0 = torch.from_numpy(x0_full[sw.row_begin:sw.row_end]).to(dev)
         outs = []
         for _ in range(steps):                       # consecutive steps reuse the two operand buffers
@@ -54,7 +54,8 @@ def _worker(rank, world, port, k, scales, steps, out_dir, f=1):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,scales,f", [(3, 0.8, 1), (4, [0.8, 1.6], 1), (1, 0.8, 1), (3, [0.8, 1.6], 16), (4, 0.8, 130)])
+@pytest.mark.parametrize("k,scales,f", [(3, 0.8, 1), (4, [0.8, 1.6], 1), (1, 0.8, 1), (3, [0.8, 1.6], -1),
+                                        (3, [0.8, 1.6], 16), (4, 0.8, 130)])
 def test_two_rank_fused_exchange_matches_oracle(tmp_path, k, scales, f):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (one process per GPU)")
@@ -63,7 +64,7 @@ def test_two_rank_fused_exchange_matches_oracle(tmp_path, k, scales, f):
     mp.spawn(_worker, args=(world, _free_port(), k, scales, steps, str(tmp_path), f), nprocs=world, join=True)
     rp, ci, n = synth.synth_csr(SHAPE, self_loops=True)
     adj = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
-    x0_full = None if f == 1 else np.random.default_rng(f).standard_normal((n, f)).astype(np.float32)
+    x0_full = None if f == 1 else np.random.default_rng(abs(f)).standard_normal((n, abs(f))).astype(np.float32)
     p = orc.wavelet_parts(adj, k=k, s=scales, x0=x0_full)
     want_h = np.concatenate(p["H"], axis=1).astype(np.float32)
     want_s = np.stack(p["S"], axis=1)                                   # [N, S, F]
