@@ -112,11 +112,9 @@ class CsrGraph:
             g = cls(rp, ci, vv, n, _prepare=False)
             g._colsum.zero_()
             g._unsorted_flag.zero_()
+            # equal row counts per piece (no host-side search over rowptr before the first copy is issued)
             pieces = max(2, min(16, nnz // cls.PIPELINE_PIECE_NNZ))
-            targets = torch.linspace(0, nnz, pieces + 1).to(torch.int64)
-            rows = torch.searchsorted(rp_h.to(torch.int64), targets, right=False).clamp_(max=n)
-            rows[0], rows[-1] = 0, n
-            rows = torch.unique_consecutive(rows).tolist()
+            rows = sorted({(n * i) // pieces for i in range(pieces + 1)})
             copy = cls._copy_stream(dev)
             copy.wait_stream(main)
             for r0, r1 in zip(rows[:-1], rows[1:]):
