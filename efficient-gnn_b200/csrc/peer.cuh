@@ -33,7 +33,7 @@ constexpr size_t kPeerErrorOff = 264;
 constexpr size_t kPeerWaitNsOff = 512;     // uint64: total ns CTA 0 spent in flag waits (diagnostic)
 constexpr size_t kPeerWaitCntOff = 520;    // uint64: number of such waits
 constexpr size_t kPeerHeaderBytes = 4096;
-constexpr unsigned long long kPeerTimeoutNs = 8000000000ull;      // 8 s: a rank that never shows up
+constexpr unsigned long long kPeerTimeoutNs = 30000000000ull;     // 30 s: a rank that never shows up
 
 struct PeerPush {
     int32_t world;                       // 0: no peer exchange
