@@ -15,12 +15,19 @@
 //     power-law graphs balance), sorted by length and packed 32 to a slice in
 //     lane-interleaved order: lane r of a warp walks virtual row r with 16-byte
 //     loads (8 indices), the warp's loads are one contiguous 512-byte segment,
-//   * stored self loops and padding point at a zero slot, so the inner loop has
-//     no predicate: load 8 indices -> 8 LDS -> 8 FADD.
+//   * stored self loops and padding point at zero slots, so the inner loop has
+//     no predicate: load 8 indices -> 8 LDS -> 8 FADD,
+//   * the order of the entries inside a virtual row is free, so it is chosen
+//     to spread the warp's 32 simultaneous gathers over the 32 banks (lane r's
+//     j-th entry sits in bank (r + j) mod 32 whenever the row has one there;
+//     3.7 -> 2.5 wavefronts per LDS on the Reddit shape), and the slices of a
+//     block are stored in a strided order of their length so every CTA's
+//     contiguous range of slices carries the same mix of long and short rows.
 // Per order: sell_spmv_kernel (persistent, one CTA per SM, entries split evenly
-// over CTAs) writes one partial sum per virtual row; sell_epilogue_kernel adds
-// each row's partials in a fixed order (deterministic), applies the Laplacian
-// scaling, the three-term recurrence and the scale accumulation.
+// over CTAs) writes one partial sum per virtual row into a row-major array;
+// sell_epilogue_kernel adds each row's partials in a fixed order
+// (deterministic), applies the Laplacian scaling, the three-term recurrence and
+// the scale accumulation.
 #pragma once
 
 #include <cub/device/device_radix_sort.cuh>
