@@ -166,6 +166,18 @@ def test_lambda_max(lam):
     check_parts(res, p["T"], p["S"], p["H"], f"lambda={lam}")
 
 
+@pytest.mark.parametrize("lam,f", [(1.5, 12), (2.7, 64), (3.3, 130)])
+def test_lambda_max_wide_signals(lam, f):
+    """lambda_max != 2 puts a non-zero diagonal in the rescaled operator: the wide kernel then needs
+    the own-row T_{k-1}, which it recovers from the pre-scaled operand (y / dinv)."""
+    c = load_case("cora_noloop")                  # has isolated nodes (dinv = 1, diagonal -1 after the shift)
+    x0 = np.random.default_rng(int(lam * 10) + f).standard_normal((c["n"], f)).astype(np.float32)
+    res = egnn.graph_wavelet_features(c["adj"], k=4, s=[0.8, 1.6], lambda_max=lam, X0=torch.from_numpy(x0),
+                                      return_parts=True)
+    p = orc.wavelet_parts(c["adj"], k=4, s=[0.8, 1.6], lambda_max=lam, x0=x0)
+    check_parts(res, p["T"], p["S"], p["H"], f"lambda={lam} F={f}")
+
+
 @pytest.mark.parametrize("shape,f,loops", [("pubmed", 1, True), ("physics", 1, False), ("physics", 16, True),
                                            ("arxiv", 1, True), ("arxiv", 8, False)])
 def test_named_shapes_against_oracle(shape, f, loops):
