@@ -18,9 +18,8 @@
 //   * stored self loops and padding point at zero slots, so the inner loop has
 //     no predicate: load 8 indices -> 8 LDS -> 8 FADD,
 //   * the order of the entries inside a virtual row is free, so it is chosen
-//     to spread the warp's 32 simultaneous gathers over the 32 banks (lane r's
-//     j-th entry sits in bank (r + j) mod 32 whenever the row has one there;
-//     3.7 -> 2.5 wavefronts per LDS on the Reddit shape), and the slices of a
+//     to spread the warp's 32 simultaneous gathers over the 32 banks (greedy
+//     edge colouring of lanes x banks per slice, see sell_fill_kernel), and the slices of a
 //     block are stored in a strided order of their length so every CTA's
 //     contiguous range of slices carries the same mix of long and short rows.
 // Per order: sell_spmv_kernel (persistent, one CTA per SM, entries split evenly
@@ -200,18 +199,24 @@ __global__ void sell_totals_kernel(const int32_t* __restrict__ slice_off, const 
 // ---- build pass 5: write the lane-interleaved 16-bit index stream -----------
 // Entry order inside a virtual row is free (the partial sum is a plain sum), so
 // it is chosen to keep the hot kernel's shared-memory gathers off each other's
-// banks: the warp's LDS for position j reads one entry per lane, and lane r
-// wants bank (r + j) mod 32 there.  Every entry goes to a position whose wanted
-// bank is its own (local column mod 32) while such positions last; the
-// overflow takes the free positions in order, and unused positions point at the
-// zero slot of the wanted bank (32 zero slots at CB .. CB+31; stored self loops
-// too).  One warp per slice: the 32 rows are placed one after the other by the
-// whole warp (coalesced reads of the CSR row, match_any for the per-bank
-// ordinals), staged in shared memory and written out with 16-byte stores.
+// banks: the warp's LDS for position j reads one entry per lane, so a slice is
+// conflict-free when, at every position, the 32 lanes hold 32 different banks
+// (bank = local column mod 32).  That is an edge colouring of the bipartite
+// multigraph lanes x banks with the positions as colours; it is done greedily
+// (first fit): lane r walks its own virtual row, and each entry takes the
+// lowest position that is free both in the lane and in the entry's bank.  One
+// warp per slice; lanes whose current entries share a bank go one at a time
+// (match_any), so a bank's position mask has one writer per round.  The few
+// entries (2-5 %) with no common free position take the lane's lowest free
+// one; unused positions point at the zero slot of bank (r + j) mod 32 (32 zero
+// slots at CB .. CB+31; stored self loops too).  Measured on the Reddit shape:
+// 3.7 wavefronts per LDS unordered, 2.5 with a fixed diagonal rule, see
+// DESIGN.md for the first-fit figure.  The 16-bit stream is written straight
+// to global memory (2-byte stores that L2 merges).
 constexpr int kSellFillWarps = 8;
 constexpr int kSellLmaxCap = 256;          // longest virtual row
-constexpr int kSellFillWarpHalves = kSellLmaxCap + 64 + 16;   // ovf + cnt + occ (uint16 units)
-constexpr size_t kSellFillSmem = (size_t)kSellFillWarps * kSellFillWarpHalves * sizeof(uint16_t);
+constexpr int kSellMaskWords = kSellLmaxCap / 32;
+constexpr size_t kSellFillSmem = (size_t)kSellFillWarps * 32 * kSellMaskWords * sizeof(uint32_t);   // bank masks
 
 __global__ void __launch_bounds__(kSellFillWarps * 32)
 sell_fill_kernel(const int32_t* __restrict__ colidx, int C, int CB, int lmax, int n_slices,
@@ -221,15 +226,12 @@ sell_fill_kernel(const int32_t* __restrict__ colidx, int C, int CB, int lmax, in
                  const int32_t* __restrict__ vp_ptr, const int32_t* __restrict__ blk_slice_ptr,
                  const int32_t* __restrict__ blk_stride, const int32_t* __restrict__ slice_off,
                  uint16_t* __restrict__ idx, int32_t* __restrict__ vslot_out, int row0) {
-    extern __shared__ __align__(16) uint16_t fill_smem[];
+    extern __shared__ __align__(16) uint32_t fill_smem[];
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
     const int s = blockIdx.x * kSellFillWarps + wid;
     if (s >= n_slices) return;
-    uint16_t* ovf = fill_smem + (size_t)wid * kSellFillWarpHalves;
-    int* cnt = reinterpret_cast<int*>(ovf + kSellLmaxCap);            // [32] entries seen per bank
-    unsigned* occ = reinterpret_cast<unsigned*>(cnt + 32);            // [8] occupied positions
-    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t* bank_used = fill_smem + (size_t)wid * 32 * kSellMaskWords;   // [bank][word]: positions taken in that bank
 
     const int c = sell_block_of_slice(blk_slice_ptr, C, s);
     const int v = s * kSellSliceRows + lane;                          // storage slot of this lane's virtual row
@@ -248,71 +250,68 @@ sell_fill_kernel(const int32_t* __restrict__ colidx, int C, int CB, int lmax, in
     const int off = slice_off[s];
     const int lpad = (slice_off[s + 1] - off) / kSellSliceRows;      // positions per lane
     const int col0 = c * CB;
+    // position j of this lane lives at idx[off + ((j >> 3) * 32 + lane) * 8 + (j & 7)]
+    uint16_t* mine = idx + off + lane * kSellGroup;
 
-    // the CSR entries of row r+1 are fetched (coalesced, <= 8 x 32) while row r is placed
-    constexpr int kBatches = kSellLmaxCap / 32;
-    int cols_next[kBatches];
-    {
-        const int l0 = __shfl_sync(0xffffffffu, len, 0), s0 = __shfl_sync(0xffffffffu, src, 0);
+    uint32_t lane_used[kSellMaskWords];                               // positions taken in this lane (>= lpad: never free)
 #pragma unroll
-        for (int t = 0; t < kBatches; ++t) cols_next[t] = (t * 32 + lane < l0) ? __ldg(colidx + s0 + t * 32 + lane) : -1;
+    for (int w = 0; w < kSellMaskWords; ++w) {
+        const int lo = w * 32;
+        lane_used[w] = lpad >= lo + 32 ? 0u : (lpad <= lo ? 0xffffffffu : ~((1u << (lpad - lo)) - 1u));
+        bank_used[lane * kSellMaskWords + w] = 0u;
     }
-    for (int r = 0; r < kSellSliceRows; ++r) {
-        const int r_len = __shfl_sync(0xffffffffu, len, r);
-        const int r_row = __shfl_sync(0xffffffffu, row, r);
-        int cols[kBatches];
-#pragma unroll
-        for (int t = 0; t < kBatches; ++t) cols[t] = cols_next[t];
-        if (r + 1 < kSellSliceRows) {
-            const int l1 = __shfl_sync(0xffffffffu, len, r + 1), s1 = __shfl_sync(0xffffffffu, src, r + 1);
-#pragma unroll
-            for (int t = 0; t < kBatches; ++t) cols_next[t] = (t * 32 + lane < l1) ? __ldg(colidx + s1 + t * 32 + lane) : -1;
+    __syncwarp();
+
+    // the lane's next CSR entry is requested one step ahead of its use
+    int i = 0, loc = -1;
+    int col_next = len > 0 ? __ldg(colidx + src) : 0;
+    while (true) {
+        while (loc < 0 && i < len) {                                  // take the next entry (skip a stored self loop)
+            const int col = col_next;
+            ++i;
+            if (i < len) col_next = __ldg(colidx + src + i);
+            if (col != row) loc = col - col0;
         }
-        // position j of row r lives at idx[off + ((j >> 3) * 32 + r) * 8 + (j & 7)]: written straight to
-        // global memory (2-byte stores that L2 merges); a shared-memory stage of the slice capped the
-        // kernel at 12 warps per SM and it was latency-bound
-        uint16_t* mine = idx + off + r * kSellGroup;
-        cnt[lane] = 0;
-        if (lane < kSellLmaxCap / 32) occ[lane] = 0u;
-        __syncwarp();
-        int n_ovf = 0;
+        const bool pending = loc >= 0;
+        if (!__any_sync(0xffffffffu, pending)) break;
+        const int b = loc & 31;
+        const unsigned grp = __match_any_sync(0xffffffffu, pending ? b : 32 + lane);
+        if (pending && (__ffs(grp) - 1) == lane) {                    // one lane per bank and round
+            uint32_t* bu = bank_used + b * kSellMaskWords;
+            int p = -1;
 #pragma unroll
-        for (int t = 0; t < kBatches; ++t) {
-            if (t * 32 < r_len) {                                     // warp-uniform
-                const int col = cols[t];
-                const int loc = (col >= 0 && col != r_row) ? col - col0 : -1;
-                const bool act = loc >= 0;
-                const int b = loc & 31;
-                const unsigned grp = __match_any_sync(0xffffffffu, act ? b : 32 + lane);
-                const int rank_in = __popc(grp & lt_mask);
-                const int base = act ? cnt[b] : 0;
-                __syncwarp();
-                if (act && rank_in == 0) cnt[b] = base + __popc(grp);
-                const int j = ((b - r) & 31) + 32 * (base + rank_in);
-                const bool placed = act && j < lpad;
-                if (placed) {
-                    mine[(j >> 3) * (kSellGroup * kSellSliceRows) + (j & 7)] = (uint16_t)loc;
-                    atomicOr(&occ[j >> 5], 1u << (j & 31));
+            for (int w = 0; w < kSellMaskWords; ++w) {
+                const uint32_t m = ~(lane_used[w] | bu[w]);
+                if (p < 0 && m) p = w * 32 + __ffs(m) - 1;
+            }
+            const bool clean = p >= 0;
+            if (!clean) {                                             // no common free position: lowest free in the lane
+#pragma unroll
+                for (int w = 0; w < kSellMaskWords; ++w) {
+                    const uint32_t m = ~lane_used[w];
+                    if (p < 0 && m) p = w * 32 + __ffs(m) - 1;
                 }
-                const unsigned om = __ballot_sync(0xffffffffu, act && !placed);
-                if (act && !placed) ovf[n_ovf + __popc(om & lt_mask)] = (uint16_t)loc;
-                n_ovf += __popc(om);
-                __syncwarp();
             }
-        }
-        int taken = 0;
-        for (int w = 0; w * 32 < lpad; ++w) {
-            const int p = w * 32 + lane;
-            const bool is_free = p < lpad && !((occ[w] >> lane) & 1u);
-            const unsigned fm = __ballot_sync(0xffffffffu, is_free);
-            if (is_free) {
-                const int kth = taken + __popc(fm & lt_mask);
-                mine[(p >> 3) * (kSellGroup * kSellSliceRows) + (p & 7)] =
-                    kth < n_ovf ? ovf[kth] : (uint16_t)(CB + ((r + p) & 31));
-            }
-            taken += __popc(fm);
+            const int wp = p >> 5;
+            const uint32_t bit = 1u << (p & 31);
+#pragma unroll
+            for (int w = 0; w < kSellMaskWords; ++w) lane_used[w] |= (w == wp) ? bit : 0u;   // stays in registers
+            if (clean) bu[wp] |= bit;
+            mine[(p >> 3) * (kSellGroup * kSellSliceRows) + (p & 7)] = (uint16_t)loc;
+            loc = -1;
         }
         __syncwarp();
+    }
+    // unused positions -> zero slot of bank (lane + p) mod 32
+#pragma unroll
+    for (int w = 0; w < kSellMaskWords; ++w) {
+        uint32_t m = ~lane_used[w];
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int p = w * 32 + bit;
+            mine[(p >> 3) * (kSellGroup * kSellSliceRows) + (p & 7)] = (uint16_t)(CB + ((lane + p) & 31));
+        }
     }
 }
 

@@ -7,9 +7,3 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 echo ncu2 rc=$?
 A="--workload arxiv --f 128 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e"
 python bench.py $A > gpurun_out/plain_arxiv.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:cheb_wide -s 10 -c 2 -f -o gpurun_out/prof_wide5_arxiv python bench.py $A > gpurun_out/ncu_arxiv.log 2>&1
-echo arxiv rc=$?
-R="--workload reddit --f 64 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
-python bench.py $R > gpurun_out/plain_r64.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:cheb_wide -s 10 -c 1 -f -o gpurun_out/prof_wide5_reddit64 python bench.py $R > gpurun_out/ncu_r64.log 2>&1
-echo reddit64 rc=$?
