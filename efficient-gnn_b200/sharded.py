@@ -19,7 +19,6 @@ the product engine is :class:`CudaEngine` (C ABI, no fallback).
 """
 from __future__ import annotations
 
-import contextlib
 import ctypes as C
 import json
 import os

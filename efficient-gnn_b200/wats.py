@@ -15,9 +15,7 @@ device every entry point raises ``EgnnError``.
 from __future__ import annotations
 
 import ctypes as C
-import math
 import time
-from typing import Optional, Sequence
 
 import numpy as np
 import torch

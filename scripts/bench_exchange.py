@@ -1,5 +1,5 @@
 """Per-order cost of the fused exchange: steps with K = 0..3 orders on the Reddit shape (torchrun)."""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 from efficient_gnn_b200 import sharded, synth

@@ -1,6 +1,6 @@
 """Rank 0's share of a W-way row partition, run alone on one GPU with a no-op
 exchange (timing only - the operand of the other ranks is garbage)."""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from efficient_gnn_b200 import sharded, synth

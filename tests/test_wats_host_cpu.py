@@ -51,3 +51,41 @@ def test_wats_mirror_reproduces_reference_numbers(name, use_gcn, self_loops):
     assert round(acc, 4) == round(float(g["acc"]), 4)
     assert round(conf, 4) == round(float(g["conf"]), 4)
     assert round(ece, 4) == round(float(g["ece"]), 4)
+
+
+def test_laplacian_operator_algebra_matches_the_reference_expressions():
+    """`(2.0 / lambda_max) * L - identity(N)` (calibration/WATS.py:55) and `2 * L` (:36) on the
+    implicit operator: only the two scalars change; anything but a multiple of I is refused."""
+    import scipy.sparse as sp
+    from efficient_gnn_b200.wats import LaplacianOperator
+
+    class FakeGraph:
+        n = 5
+
+    L = LaplacianOperator(FakeGraph())
+    assert (L.scale, L.shift, L.shape) == (1.0, 0.0, (5, 5))
+    Lr = (2.0 / 2.0) * L - sp.identity(5)
+    assert (Lr.scale, Lr.shift) == (1.0, -1.0)
+    L3 = (2.0 / 3.0) * L - sp.identity(5)
+    assert L3.scale == pytest.approx(2.0 / 3.0) and L3.shift == -1.0
+    twice = 2 * Lr
+    assert (twice.scale, twice.shift) == (2.0, -2.0)
+    same = L.rescaled(3.0)
+    assert same.scale == pytest.approx(L3.scale) and same.shift == L3.shift
+    plus = Lr + 0.5 * sp.identity(5)
+    assert plus.shift == -0.5
+    with pytest.raises(ValueError):
+        L - sp.csr_matrix(np.ones((5, 5)))
+    with pytest.raises(ValueError):
+        L - sp.identity(4)
+    with pytest.raises(TypeError):
+        L - 1.0
+
+
+def test_heat_coefficients_shapes_and_values():
+    from efficient_gnn_b200.wats import heat_coefficients
+    c = heat_coefficients(3, [0.4, 0.8, 1.6])
+    assert c.shape == (3, 4) and c.dtype == np.float64
+    np.testing.assert_allclose(c[:, 0], 1.0)
+    np.testing.assert_allclose(c[1], np.exp(-0.8 * np.arange(4)))
+    assert heat_coefficients(0, 0.8).shape == (1, 1)
