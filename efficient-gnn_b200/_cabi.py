@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libegnn_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # every symbol include/egnn_b200.h declares: name -> (restype, argtypes)
 _P, _I32, _I64, _F32, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -33,14 +33,14 @@ SYMBOLS = {
     "egnn_sell_ws_bytes": (_SZ, [_I64, _I64, _I32, _I32]),
     "egnn_sell_prepare": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _SZ, _P]),
     "egnn_sell_fill": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _SZ, _P]),
-    "egnn_patch_degrees": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _P, _P, _P, _P]),
+    "egnn_patch_degrees": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _P, _P, _P, _I64, _I64, _P]),
     "egnn_cheb_workspace_bytes": (_SZ, [_I64, _I32]),
     "egnn_cheb_wavelet": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, _F32, _F32,
                                     _P, _P, _I32, _P, _P, _P, _I32, _P, _SZ, _P, _P, _P, _P]),
     "egnn_row_order_ws_bytes": (_SZ, [_I64]),
     "egnn_row_order": (C.c_int, [_P, _I64, _P, _P, _SZ, _P]),
-    "egnn_sell_order_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _F32, _F32,
-                                          _I32, _P, _P]),
+    "egnn_sell_step_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P,
+                                         _F32, _F32, _I32, _P, _P, _P, _I32, _P, _P]),
     "egnn_peer_window_bytes": (_SZ, [_I64, _I32, _I32]),
     "egnn_peer_alloc": (C.c_int, [_SZ, _P, _P]),
     "egnn_peer_open": (C.c_int, [_P, _P]),
@@ -51,12 +51,12 @@ SYMBOLS = {
     "egnn_peer_wait_stats": (C.c_int, [_P, _P, _P, _I32, _P]),
     "egnn_peer_prescale_push": (C.c_int, [_P, _P, _I64, _I64, _I32, _P, _P]),
     "egnn_wide_order_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _I32,
-                                          _P, _F32, _F32, _I32, _P, _P]),
+                                          _P, _F32, _F32, _I32, _P, _P, _P, _I32, _P, _P]),
     "egnn_prescale": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P]),
-    "egnn_graph_prep_sharded": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "egnn_graph_prep_sharded": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "egnn_cheb_order_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                           _I64, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _P, _F32, _F32,
-                                          _I32, _I32, _P]),
+                                          _I32, _I32, _P, _P, _P, _I32, _P]),
 }
 
 
@@ -66,7 +66,8 @@ class SellPlanStruct(C.Structure):
                 ("n_cols", C.c_int32), ("row0", C.c_int32), ("n_cta", C.c_int32), ("reserved", C.c_int32),
                 ("n_slices", C.c_int64), ("n_vrows", C.c_int64), ("n_entries", C.c_int64), ("n_rowv", C.c_int64),
                 ("slice_off", C.c_void_p), ("blk_slice_ptr", C.c_void_p), ("idx", C.c_void_p),
-                ("rv_ptr", C.c_void_p), ("vslot", C.c_void_p), ("cta_ptr", C.c_void_p), ("vpart", C.c_void_p)]
+                ("rv_ptr", C.c_void_p), ("vslot", C.c_void_p), ("cta_info", C.c_void_p), ("vpart", C.c_void_p),
+                ("sched", C.c_void_p), ("stamps", C.c_void_p)]
 
 
 MAX_RANKS = 16

@@ -11,6 +11,7 @@
 #include "peer.cuh"
 #include "prep.cuh"
 #include "sell.cuh"
+#include "sell_step.cuh"
 #include "wide.cuh"
 
 namespace egnn {
@@ -107,18 +108,24 @@ static RingConfig ring_config(int ldy) {
     return c;
 }
 
-template <int NZ_LOG2>
-static int launch_wide_n(const WideParams& p, dim3 grid, cudaStream_t st) {
+template <int NZ_LOG2, bool PEER>
+static int launch_wide_np(const WideParams& p, dim3 grid, cudaStream_t st) {
     const bool aligned = (p.F % 4) == 0;
     if (p.vals) {
-        if (aligned) cheb_wide_kernel<NZ_LOG2, true, true><<<grid, kWideBlock, 0, st>>>(p);
-        else cheb_wide_kernel<NZ_LOG2, true, false><<<grid, kWideBlock, 0, st>>>(p);
+        if (aligned) cheb_wide_kernel<NZ_LOG2, true, true, PEER><<<grid, kWideBlock, 0, st>>>(p);
+        else cheb_wide_kernel<NZ_LOG2, true, false, PEER><<<grid, kWideBlock, 0, st>>>(p);
     } else {
-        if (aligned) cheb_wide_kernel<NZ_LOG2, false, true><<<grid, kWideBlock, 0, st>>>(p);
-        else cheb_wide_kernel<NZ_LOG2, false, false><<<grid, kWideBlock, 0, st>>>(p);
+        if (aligned) cheb_wide_kernel<NZ_LOG2, false, true, PEER><<<grid, kWideBlock, 0, st>>>(p);
+        else cheb_wide_kernel<NZ_LOG2, false, false, PEER><<<grid, kWideBlock, 0, st>>>(p);
     }
     EGNN_LAUNCH_CHECK("cheb_wide_kernel launch");
     return EGNN_OK;
+}
+
+// PEER instantiation: operand in the exchange window, written by the other GPUs (world > 1)
+template <int NZ_LOG2>
+static int launch_wide_n(const WideParams& p, dim3 grid, cudaStream_t st) {
+    return p.peer.world > 1 ? launch_wide_np<NZ_LOG2, true>(p, grid, st) : launch_wide_np<NZ_LOG2, false>(p, grid, st);
 }
 
 // Wide kernel: persistent grid of kWideMinBlocks CTAs per SM per feature tile.
@@ -240,34 +247,62 @@ static void fill_peer_push(PeerPush& pp, const egnn_peer_window* w, int which, b
     pp.error = (unsigned*)(own + kPeerErrorOff);
 }
 
-// The narrow-path SpMV: 8 x 16-byte index loads in flight per lane.  `win`
-// non-NULL: the operand is this rank's exchange window (wait for the peers first).
-static int launch_sell_spmv(const egnn_sell_plan* pl, const float* y, int n_cols, cudaStream_t st,
-                            const egnn_peer_window* win = nullptr, int which = 0) {
-    const size_t smem = sizeof(float) * ((size_t)pl->col_block + kSellZeroSlots);
-    const int sms = pl->n_cta;
-    SellPeerWait pw{};
-    if (win && win->world > 1) {
-        char* own = (char*)win->base[win->rank];
-        pw.local_flags = (const unsigned*)(own + kPeerFlagsOff);
-        pw.epoch = (const unsigned*)(own + kPeerEpochOff);
-        pw.error = (unsigned*)(own + kPeerErrorOff);
-        pw.world = win->world; pw.rank = win->rank;
-        int rc = check_cuda(cudaFuncSetAttribute(sell_spmv_kernel<kSellUnroll, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem), "cudaFuncSetAttribute(sell_spmv_kernel)");
+// ---- the narrow-path step kernel (sell_step.cuh) ------------------------------
+static void step_fill_plan(SellStepParams& sp, const egnn_sell_plan* pl) {
+    sp.idx = pl->idx; sp.slice_off = pl->slice_off; sp.blk_slice_ptr = pl->blk_slice_ptr; sp.vslot = pl->vslot;
+    sp.cta_info = pl->cta_info; sp.rv_ptr = pl->rv_ptr; sp.vpart = pl->vpart; sp.sched = pl->sched;
+    sp.stamps = (unsigned long long*)pl->stamps;
+    sp.trace = pl->reserved;          // diagnostic: per-CTA trace behind the stamps (scripts/time_step.py)
+    sp.n_cta = pl->n_cta; sp.C = pl->n_blocks; sp.CB = pl->col_block; sp.n_cols = pl->n_cols;
+    sp.n_rows = pl->n; sp.row0 = pl->row0;
+}
+
+static void step_fill_peer(SellStepParams& sp, const egnn_peer_window* w) {
+    sp.world = w->world; sp.rank = w->rank; sp.rows_per = w->rows_per;
+    char* own = (char*)w->base[w->rank];
+    for (int r = 0; r < w->world; ++r) sp.flag_at[r] = (unsigned*)((char*)w->base[r] + kPeerFlagsOff) + w->rank;
+    sp.local_flags = (unsigned*)(own + kPeerFlagsOff);
+    sp.epoch = (unsigned*)(own + kPeerEpochOff);
+    sp.error = (unsigned*)(own + kPeerErrorOff);
+}
+
+// One cooperative launch: every CTA must be resident (grid barriers, and - row-sharded - flag
+// waits on the other GPUs), one CTA per SM.
+static int launch_sell_step(const SellStepParams& sp, bool peer, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)sp.CB + kSellZeroSlots);
+    const void* fn = peer ? (const void*)sell_step_kernel<true> : (const void*)sell_step_kernel<false>;
+    int rc = check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        "cudaFuncSetAttribute(sell_step_kernel)");
+    if (rc) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)sp.n_cta, 1, 1);
+    cfg.blockDim = dim3(kSellThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    void* args[1] = {(void*)&sp};
+    return check_cuda(cudaLaunchKernelExC(&cfg, fn, args), "sell_step_kernel launch");
+}
+
+// Launches the orders order_begin..order_end (default 1..k) of one step in chunks of
+// kStepMaxOrders.  `sp` carries everything but the order window.
+static int run_sell_step(SellStepParams sp, int k, int n_scales, const float* coeffs_host, bool peer, cudaStream_t st,
+                         int order_begin = 1, int order_end = -1) {
+    if (order_end < 0) order_end = k;
+    const float* held = sp.operand_first;
+    for (int ob = order_begin; ob <= order_end; ob += kStepMaxOrders) {
+        const int oe = ob + kStepMaxOrders - 1 < order_end ? ob + kStepMaxOrders - 1 : order_end;
+        sp.order_begin = ob; sp.order_end = oe; sp.k_max = k; sp.S = n_scales;
+        sp.operand_first = ob == order_begin ? held : nullptr;
+        for (int s = 0; s < n_scales; ++s)
+            for (int j = 0; j <= oe - ob + 1; ++j) sp.coef[s][j] = coeffs_host[s * (k + 1) + ob - 1 + j];
+        int rc = launch_sell_step(sp, peer, st);
         if (rc) return rc;
-        sell_spmv_kernel<kSellUnroll, true><<<sms, kSellThreads, smem, st>>>(
-            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->cta_ptr, pl->n_cta, pl->n_blocks, pl->col_block,
-            peer_operand(win, win->rank, which), n_cols, pl->vpart, pw);
-    } else {
-        int rc = check_cuda(cudaFuncSetAttribute(sell_spmv_kernel<kSellUnroll, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem), "cudaFuncSetAttribute(sell_spmv_kernel)");
-        if (rc) return rc;
-        sell_spmv_kernel<kSellUnroll, false><<<sms, kSellThreads, smem, st>>>(
-            pl->idx, pl->slice_off, pl->blk_slice_ptr, pl->vslot, pl->cta_ptr, pl->n_cta, pl->n_blocks, pl->col_block,
-            y, n_cols, pl->vpart, pw);
     }
-    EGNN_LAUNCH_CHECK("sell_spmv_kernel launch");
     return EGNN_OK;
 }
 
@@ -283,7 +318,7 @@ using namespace egnn;
 
 extern "C" {
 
-int egnn_abi_version(void) { return 3; }
+int egnn_abi_version(void) { return 4; }
 
 const char* egnn_last_error(void) { return last_error_buf(); }
 
@@ -387,9 +422,10 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base, const floa
                        const uint8_t* iso_base, const float* x0_base, int64_t n,
                        const int32_t* delta_row_host, const int32_t* delta_col_host,
                        const float* delta_val_host, int32_t n_delta, float* dinv_out, uint8_t* iso_out,
-                       float* x0_out, egnn_stream_t stream) {
-    EGNN_REQUIRE(w_base && rowsum_base && dinv_base && iso_base && x0_base && dinv_out && iso_out && x0_out,
-                 "null pointer");
+                       float* x0_out, int64_t row_begin, int64_t n_rows, egnn_stream_t stream) {
+    EGNN_REQUIRE(w_base && dinv_base && iso_base && dinv_out && iso_out, "null pointer");
+    EGNN_REQUIRE(row_begin >= 0 && n_rows >= 0 && row_begin + n_rows <= n, "bad row range");
+    EGNN_REQUIRE(n_rows == 0 || (rowsum_base && x0_base && x0_out), "null pointer");
     DeltaList d;
     int rc = fill_delta(d, delta_row_host, delta_col_host, delta_val_host, n_delta);
     if (rc) return rc;
@@ -400,10 +436,12 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base, const floa
     if (rc) return rc;
     rc = check_cuda(cudaMemcpyAsync(iso_out, iso_base, sizeof(uint8_t) * n, cudaMemcpyDeviceToDevice, st), "copy iso");
     if (rc) return rc;
-    rc = check_cuda(cudaMemcpyAsync(x0_out, x0_base, sizeof(float) * n, cudaMemcpyDeviceToDevice, st), "copy x0");
-    if (rc) return rc;
+    if (n_rows > 0) {
+        rc = check_cuda(cudaMemcpyAsync(x0_out, x0_base, sizeof(float) * n_rows, cudaMemcpyDeviceToDevice, st), "copy x0");
+        if (rc) return rc;
+    }
     if (n_delta > 0) {
-        patch_degrees_kernel<<<1, EGNN_MAX_DELTA, 0, st>>>(w_base, rowsum_base, d, dinv_out, iso_out, x0_out);
+        patch_degrees_kernel<<<1, EGNN_MAX_DELTA, 0, st>>>(w_base, rowsum_base, d, dinv_out, iso_out, x0_out, row_begin, n_rows);
         EGNN_LAUNCH_CHECK("patch_degrees_kernel launch");
     }
     return EGNN_OK;
@@ -512,7 +550,7 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
         rc = check_cuda(cudaMemcpyAsync(t_all_or_null, x0, sizeof(float) * slab_elems, cudaMemcpyDeviceToDevice, st), "copy T0");
         if (rc) return rc;
     }
-    if (cfg.prescaled) {
+    if (cfg.prescaled && !sell_plan) {
         prescale_kernel<<<grid_for((int64_t)slab_elems, 256), 256, 0, st>>>(x0, dinv, ybuf[0], n, f, 0);
         EGNN_LAUNCH_CHECK("prescale_kernel launch");
     }
@@ -520,46 +558,29 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
     if (sell_plan) {
         EGNN_REQUIRE(f == 1 && vals_or_null == nullptr, "the SELL plan serves F = 1 on a binary adjacency");
         EGNN_REQUIRE(sell_plan->n == n && sell_plan->n_cols == n && sell_plan->row0 == 0 && sell_plan->vpart && sell_plan->slice_off && sell_plan->blk_slice_ptr &&
-                     sell_plan->rv_ptr && sell_plan->vslot && sell_plan->cta_ptr, "SELL plan does not match the graph or is not filled");
-        SellEpilogueParams ep{};
-        ep.delta = p.delta;
-        ep.rv_ptr = sell_plan->rv_ptr; ep.vpart = sell_plan->vpart;
-        ep.dinv = dinv; ep.iso = iso; ep.out = out; ep.n = (int32_t)n; ep.S = n_scales; ep.row0 = 0;
-        ep.a = op_scale; ep.b = op_shift;
-        const float* t_prev = x0;
-        const float* t_prev2 = nullptr;
-        for (int order = 1; order <= k; ++order) {
-            const bool last = order == k;
-            float* t_out;
-            if (t_all_or_null) t_out = t_all_or_null + (size_t)order * slab_elems;
-            else if (last) t_out = nullptr;
-            else if (order == 1) t_out = tbuf[0];
-            else if (order == 2) t_out = tbuf[1];
-            else t_out = const_cast<float*>(t_prev2);
-            const float* y_prev = ybuf[(order - 1) & 1];
-            if (order_events_host) {
-                rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1)], st), "event record");
+                     sell_plan->rv_ptr && sell_plan->vslot && sell_plan->cta_info && sell_plan->sched, "SELL plan does not match the graph or is not filled");
+        // all K orders in one persistent launch (sell_step.cuh); the first operand dinv (.) T_0 is
+        // computed inside it
+        SellStepParams sp{};
+        step_fill_plan(sp, sell_plan);
+        sp.delta = p.delta;
+        sp.dinv = dinv; sp.iso = iso; sp.x0 = x0; sp.operand_first = nullptr;
+        sp.operand[0] = ybuf[0]; sp.operand[1] = ybuf[1];
+        sp.ydst[0][0] = ybuf[0]; sp.ydst[1][0] = ybuf[1]; sp.n_dst = 1;
+        sp.tbuf[0] = tbuf[0]; sp.tbuf[1] = tbuf[1]; sp.t_all = t_all_or_null; sp.out = out;
+        sp.normalize = normalize_l1; sp.a = op_scale; sp.b = op_shift;
+        sp.world = 1; sp.rank = 0; sp.rows_per = n;
+        if (order_events_host) {
+            rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[0], st), "event record");
+            if (rc) return rc;
+        }
+        rc = run_sell_step(sp, k, n_scales, coeffs_host, false, st);
+        if (rc) return rc;
+        if (order_events_host) {                      // one launch: events 0 and 1 bracket the whole step, the rest follow it
+            for (int e = 1; e < 2 * k; ++e) {
+                rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[e], st), "event record");
                 if (rc) return rc;
             }
-            if (sell_plan->n_slices > 0) {
-                rc = launch_sell_spmv(sell_plan, y_prev, (int)n, st);
-                if (rc) return rc;
-            }
-            if (order_events_host) {
-                rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1) + 1], st), "event record");
-                if (rc) return rc;
-            }
-            ep.y_prev = y_prev; ep.tprev = t_prev; ep.tprev2 = t_prev2; ep.tk = t_out;
-            ep.y_out = last ? nullptr : ybuf[order & 1];
-            ep.first = order == 1; ep.normalize = last && normalize_l1;
-            for (int s = 0; s < n_scales; ++s) {
-                ep.c_prev[s] = coeffs_host[s * (k + 1) + order - 1];
-                ep.c_k[s] = coeffs_host[s * (k + 1) + order];
-            }
-            sell_epilogue_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(ep);
-            EGNN_LAUNCH_CHECK("sell_epilogue_kernel launch");
-            t_prev2 = t_prev;
-            t_prev = t_out;
         }
         return EGNN_OK;
     }
@@ -663,7 +684,9 @@ int egnn_cheb_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
                             float* out_local, float* acc_ws, int64_t n, int64_t nnz_hint,
                             int64_t row_begin, int64_t row_end, int32_t f, int32_t order, int32_t k_max,
                             int32_t n_scales, const float* coeffs_host, float op_scale, float op_shift,
-                            int32_t normalize_l1, int32_t phase, egnn_stream_t stream) {
+                            int32_t normalize_l1, int32_t phase,
+                            const int32_t* delta_row_host, const int32_t* delta_col_host,
+                            const float* delta_val_host, int32_t n_delta, egnn_stream_t stream) {
     EGNN_REQUIRE(dinv_full && iso_full && out_local && coeffs_host && t_prev_local, "null pointer");
     EGNN_REQUIRE(row_begin >= 0 && row_end >= row_begin && row_end <= n, "bad row range");
     EGNN_REQUIRE(order >= 1 && order <= k_max && k_max <= EGNN_MAX_ORDER, "bad order");
@@ -676,6 +699,13 @@ int egnn_cheb_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
 
     OrderParams p{};
     p.delta.n = 0;
+    if (phase != 0) {                 // edge flips ride with the launch that gathers from the exchanged operand
+        int drc = fill_delta(p.delta, delta_row_host, delta_col_host, delta_val_host, n_delta);
+        if (drc) return drc;
+        for (int i = 0; i < n_delta; ++i)
+            EGNN_REQUIRE(p.delta.row[i] >= 0 && p.delta.row[i] < n && p.delta.col[i] >= 0 && p.delta.col[i] < n,
+                         "delta index out of range");
+    }
     p.vals = nullptr; p.dinv = dinv_full; p.iso = iso_full;
     p.tprev_own = t_prev_local; p.tprev2_own = t_prev2_local; p.tk_own = t_out_local; p.y_own = nullptr;
     p.out = out_local; p.acc_ws = acc_ws; p.n_rows = rows; p.row0 = row_begin; p.F = f; p.S = n_scales;
@@ -791,7 +821,7 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
     int rc = sell_check_geometry(n, nnz, plan);
     if (rc) return rc;
     (void)rowptr;
-    EGNN_REQUIRE(plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr && plan->cta_ptr, "plan buffers not allocated");
+    EGNN_REQUIRE(plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr && plan->cta_info && plan->sched, "plan buffers not allocated");
     EGNN_REQUIRE(plan->n_cta >= 1 && plan->n_cta <= 4096, "n_cta out of range");
     EGNN_REQUIRE(plan->n_entries == 0 || plan->idx, "plan idx not allocated");
     EGNN_REQUIRE(plan->n_vrows == 0 || plan->vslot, "plan vslot not allocated");
@@ -805,9 +835,8 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
     rc = check_cuda(cudaMemcpyAsync(plan->slice_off, w.slice_off, 4 * (plan->n_slices + 1), cudaMemcpyDeviceToDevice, st), "copy slice_off"); if (rc) return rc;
     rc = check_cuda(cudaMemcpyAsync(plan->blk_slice_ptr, w.bsp, 4 * (C + 1), cudaMemcpyDeviceToDevice, st), "copy blk_slice_ptr"); if (rc) return rc;
     rc = check_cuda(cudaMemcpyAsync(plan->rv_ptr, w.rv_ptr, 4 * (n + 1), cudaMemcpyDeviceToDevice, st), "copy rv_ptr"); if (rc) return rc;
-    sell_cta_ranges_kernel<<<(unsigned)ceil_div64(plan->n_cta + 1, 256), 256, 0, st>>>(w.slice_off, w.bsp, C, (int)plan->n_slices,
-                                                                                  plan->n_cta, plan->cta_ptr);
-    EGNN_LAUNCH_CHECK("sell_cta_ranges_kernel launch");
+    sell_cta_blocks_kernel<<<1, 32, 0, st>>>(w.slice_off, w.bsp, C, plan->n_cta, plan->cta_info, plan->sched);
+    EGNN_LAUNCH_CHECK("sell_cta_blocks_kernel launch");
     if (plan->n_slices > 0) {
         rc = check_cuda(cudaFuncSetAttribute(sell_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSellFillSmem),
                         "cudaFuncSetAttribute(sell_fill_kernel)");
@@ -820,60 +849,64 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
     return EGNN_OK;
 }
 
-int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full, const float* dinv_full,
-                            const uint8_t* iso_full, const float* t_prev_local, const float* t_prev2_local,
-                            float* t_out_local, float* y_out_local, float* out_local, int32_t order,
-                            int32_t k_max, int32_t n_scales, const float* coeffs_host, float op_scale,
-                            float op_shift, int32_t normalize_l1, egnn_stream_t stream,
-                            const egnn_peer_window* win) {
-    EGNN_REQUIRE(plan && dinv_full && iso_full && t_prev_local && out_local && coeffs_host, "null pointer");
-    EGNN_REQUIRE(win || y_prev_full, "operand missing");
-    EGNN_REQUIRE(plan->vpart && plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr && plan->vslot && plan->cta_ptr, "SELL plan is not filled");
-    EGNN_REQUIRE(order >= 1 && order <= k_max && k_max <= EGNN_MAX_ORDER, "bad order");
+int egnn_sell_step_sharded(const egnn_sell_plan* plan, const float* dinv_full, const uint8_t* iso_full,
+                           const float* x0_local, const float* y_first_full, float* y_slab0, float* y_slab1,
+                           float* tbuf0, float* tbuf1, float* t_all_or_null, float* out_local,
+                           int32_t order_begin, int32_t order_end, int32_t k_max, int32_t n_scales,
+                           const float* coeffs_host, float op_scale, float op_shift, int32_t normalize_l1,
+                           const int32_t* delta_row_host, const int32_t* delta_col_host,
+                           const float* delta_val_host, int32_t n_delta,
+                           const egnn_peer_window* win, egnn_stream_t stream) {
+    EGNN_REQUIRE(plan && dinv_full && iso_full && out_local && coeffs_host, "null pointer");
+    EGNN_REQUIRE(plan->vpart && plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr && plan->vslot && plan->cta_info && plan->sched,
+                 "SELL plan is not filled");
+    EGNN_REQUIRE(order_begin >= 1 && order_begin <= order_end && order_end <= k_max && k_max <= EGNN_MAX_ORDER, "bad order range");
     EGNN_REQUIRE(n_scales >= 1 && n_scales <= EGNN_MAX_SCALES, "n_scales out of range");
-    EGNN_REQUIRE(order == 1 || t_prev2_local, "T_{k-2} missing");
+    EGNN_REQUIRE(plan->n == 0 || x0_local, "T_0 rows missing");
+    EGNN_REQUIRE(t_all_or_null || k_max == 1 || (tbuf0 && tbuf1), "T buffers missing");
+    const bool fused = win && win->world > 1;
     if (win) {
         int rc = peer_check(win);
         if (rc) return rc;
         EGNN_REQUIRE(win->f == 1 && (int64_t)win->world * win->rows_per >= plan->n_cols &&
                      (int64_t)plan->row0 + plan->n <= (int64_t)win->world * win->rows_per, "window does not fit the plan");
-    }
-    const bool fused = win && win->world > 1;
-    if (plan->n == 0 && !fused) return EGNN_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    // operand: the caller's full vector when given (also with a window: an operand every rank
-    // already holds, e.g. the default signal at order 1, needs no exchange and no wait), else
-    // buffer (order-1)&1 of the window
-    const bool from_window = win && !y_prev_full;
-    const float* operand = from_window ? peer_operand(win, win->rank, (order - 1) & 1) : y_prev_full;
-    if (plan->n_slices > 0 || (fused && from_window)) {
-        int rc = launch_sell_spmv(plan, operand, plan->n_cols, st, from_window ? win : nullptr, (order - 1) & 1);
-        if (rc) return rc;
-    }
-    SellEpilogueParams ep{};
-    ep.delta.n = 0;
-    ep.rv_ptr = plan->rv_ptr; ep.vpart = plan->vpart; ep.y_prev = operand;
-    ep.dinv = dinv_full; ep.iso = iso_full; ep.tprev = t_prev_local; ep.tprev2 = t_prev2_local;
-    ep.tk = t_out_local; ep.y_out = win ? nullptr : y_out_local; ep.out = out_local;
-    ep.n = plan->n; ep.S = n_scales; ep.first = order == 1; ep.normalize = (order == k_max) && normalize_l1;
-    ep.row0 = plan->row0; ep.a = op_scale; ep.b = op_shift;
-    for (int s = 0; s < n_scales; ++s) {
-        ep.c_prev[s] = coeffs_host[s * (k_max + 1) + order - 1];
-        ep.c_k[s] = coeffs_host[s * (k_max + 1) + order];
-    }
-    if (win) {
-        fill_peer_push(ep.peer, win, order & 1, order < k_max, false);
-        if (win->world == 1 && order < k_max) ep.y_out = peer_operand(win, 0, order & 1);   // single rank: plain store
-    }
-    if (fused) {                                    // one CTA per SM: one system fence per SM (sell.cuh)
-        int64_t blocks = ceil_div64(plan->n > 0 ? plan->n : 1, 1024);
-        if (blocks > plan->n_cta) blocks = plan->n_cta;
-        sell_epilogue_kernel<<<(unsigned)blocks, 1024, 0, st>>>(ep);
     } else {
-        sell_epilogue_kernel<<<(unsigned)ceil_div64(plan->n > 0 ? plan->n : 1, 256), 256, 0, st>>>(ep);
+        // without a window one launch covers one order: the caller exchanges the operand in between
+        EGNN_REQUIRE(plan->n == plan->n_cols || (order_begin == order_end && y_first_full),
+                     "a row shard without an exchange window runs one order per call on a gathered operand");
+        EGNN_REQUIRE(order_end == k_max || (y_slab0 && y_slab1), "operand slabs missing");
     }
-    EGNN_LAUNCH_CHECK("sell_epilogue_kernel launch");
-    return EGNN_OK;
+    SellStepParams sp{};
+    int rc = fill_delta(sp.delta, delta_row_host, delta_col_host, delta_val_host, n_delta);
+    if (rc) return rc;
+    for (int i = 0; i < n_delta; ++i)
+        EGNN_REQUIRE(sp.delta.row[i] >= 0 && sp.delta.row[i] < plan->n_cols && sp.delta.col[i] >= 0 && sp.delta.col[i] < plan->n_cols,
+                     "delta index out of range");
+    step_fill_plan(sp, plan);
+    sp.dinv = dinv_full; sp.iso = iso_full; sp.x0 = x0_local; sp.operand_first = y_first_full;
+    sp.tbuf[0] = tbuf0; sp.tbuf[1] = tbuf1; sp.t_all = t_all_or_null; sp.out = out_local;
+    sp.normalize = normalize_l1; sp.a = op_scale; sp.b = op_shift;
+    sp.world = 1; sp.rank = 0; sp.rows_per = plan->n_cols;
+    if (win) {
+        // operand buffers live in the exchange windows: order k reads buffer (k-1)&1 of the own
+        // window, its epilogue stores dinv (.) T_k into buffer k&1 of EVERY rank's window
+        step_fill_peer(sp, win);
+        for (int b = 0; b < 2; ++b) {
+            sp.operand[b] = peer_operand(win, win->rank, b);
+            for (int r = 0; r < win->world; ++r) sp.ydst[b][r] = peer_operand(win, r, b);
+        }
+        sp.n_dst = win->world;
+    } else {
+        // operand slabs hold only the own rows: shifted so that the global row index lands in them
+        float* slab[2] = {y_slab0, y_slab1};
+        for (int b = 0; b < 2; ++b) {
+            sp.operand[b] = nullptr;
+            sp.ydst[b][0] = slab[b] ? (float*)((uintptr_t)slab[b] - sizeof(float) * (size_t)plan->row0) : nullptr;
+        }
+        if (plan->n == plan->n_cols) { sp.operand[0] = y_slab0; sp.operand[1] = y_slab1; }
+        sp.n_dst = 1;
+    }
+    return run_sell_step(sp, k_max, n_scales, coeffs_host, fused, (cudaStream_t)stream, order_begin, order_end);
 }
 
 size_t egnn_calibration_metrics_ws_bytes(int32_t n_classes, int32_t n_bins) {
@@ -1031,7 +1064,9 @@ int egnn_wide_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
                             const float* x0_local, float* t_out_local_or_null, float* out_local, int64_t n_global,
                             int64_t row_begin, int64_t row_end, int32_t f, int32_t order, int32_t k_max,
                             int32_t n_scales, const float* coeffs_host, float op_scale, float op_shift,
-                            int32_t normalize_l1, const egnn_peer_window* win, egnn_stream_t stream) {
+                            int32_t normalize_l1, const int32_t* delta_row_host, const int32_t* delta_col_host,
+                            const float* delta_val_host, int32_t n_delta, const egnn_peer_window* win,
+                            egnn_stream_t stream) {
     EGNN_REQUIRE(rowptr_local && dinv_full && iso_full && out_local && coeffs_host && win, "null pointer");
     EGNN_REQUIRE(row_begin >= 0 && row_end >= row_begin && row_end <= n_global, "bad row range");
     EGNN_REQUIRE(f >= kWideMinF, "the wide sharded order serves f >= 8");
@@ -1046,7 +1081,11 @@ int egnn_wide_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
     const int64_t rows = row_end - row_begin;
     const RingConfig rcfg = ring_config(ldy);
     WideParams wp{};
-    wp.delta.n = 0;
+    rc = fill_delta(wp.delta, delta_row_host, delta_col_host, delta_val_host, n_delta);
+    if (rc) return rc;
+    for (int i = 0; i < n_delta; ++i)
+        EGNN_REQUIRE(wp.delta.row[i] >= 0 && wp.delta.row[i] < n_global && wp.delta.col[i] >= 0 && wp.delta.col[i] < n_global,
+                     "delta index out of range");
     wp.rowptr = rowptr_local; wp.colidx = colidx_local; wp.vals = vals_or_null;
     wp.perm = row_order_or_null; wp.n_hub = row_order_or_null ? row_order_or_null + rows : nullptr;
     wp.dinv = dinv_full; wp.iso = iso_full; wp.out = out_local; wp.n_rows = rows; wp.row0 = row_begin;
@@ -1079,7 +1118,7 @@ int egnn_graph_prep_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
                             int64_t n_global, int64_t row_begin, int64_t n_rows, int32_t phase,
                             double* colsum_full, float* diag_full, float* rowsum_local, float* dinv_full,
                             uint8_t* iso_full, float* x0_local, int32_t* unsorted_flag_or_null,
-                            egnn_stream_t stream) {
+                            float* w_full_or_null, egnn_stream_t stream) {
     EGNN_REQUIRE(colsum_full && diag_full && rowsum_local, "null pointer");
     EGNN_REQUIRE(n_global >= 0 && row_begin >= 0 && n_rows >= 0 && row_begin + n_rows <= n_global, "bad row range");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1105,7 +1144,7 @@ int egnn_graph_prep_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
     EGNN_REQUIRE(phase == 1 && dinv_full && iso_full, "bad phase or null outputs");
     if (n_global > 0) {    // after the all-reduce: normaliser of every node, x0 of the local rows
         normaliser_kernel<<<(unsigned)ceil_div64(n_global, 256), 256, 0, st>>>(colsum_full, diag_full, nullptr, n_global,
-                                                                            dinv_full, iso_full, nullptr, nullptr);
+                                                                            dinv_full, iso_full, nullptr, w_full_or_null);
         EGNN_LAUNCH_CHECK("normaliser_kernel launch");
     }
     if (x0_local && n_rows > 0) {

@@ -206,10 +206,12 @@ struct DeltaList {
 
 // UGCA recompute: re-derive dinv/iso/x0 of the <= 2*budget nodes an edge flip
 // touches (the *_out vectors already hold a copy of the base graph's).
+// Row-sharded: w/dinv/iso are full-length (replicated), rowsum/x0 hold the rows
+// [row_begin, row_begin + n_rows) only.
 __global__ void patch_degrees_kernel(const float* __restrict__ w_base,
                                      const float* __restrict__ rowsum_base, DeltaList d,
                                      float* __restrict__ dinv_out, uint8_t* __restrict__ iso_out,
-                                     float* __restrict__ x0_out) {
+                                     float* __restrict__ x0_out, int64_t row_begin, int64_t n_rows) {
     const int e = threadIdx.x;
     if (e >= d.n) return;
     // in-degree of node col[e]: handled by the first delta naming that column
@@ -233,11 +235,11 @@ __global__ void patch_degrees_kernel(const float* __restrict__ w_base,
         const int u = d.row[e];
         bool first = true;
         for (int j = 0; j < e; ++j) first &= (d.row[j] != u);
-        if (first) {
+        if (first && u >= row_begin && u < row_begin + n_rows) {
             float dr = 0.f;
             for (int j = 0; j < d.n; ++j)
                 if (d.row[j] == u) dr += d.val[j];
-            x0_out[u] = (float)log1p((double)(rowsum_base[u] + dr));
+            x0_out[u - row_begin] = (float)log1p((double)(rowsum_base[u - row_begin] + dr));
         }
     }
 }

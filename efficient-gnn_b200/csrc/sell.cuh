@@ -20,13 +20,15 @@
 //   * the order of the entries inside a virtual row is free, so it is chosen
 //     to spread the warp's 32 simultaneous gathers over the 32 banks (greedy
 //     edge colouring of lanes x banks per slice, see sell_fill_kernel), and the slices of a
-//     block are stored in a strided order of their length so every CTA's
-//     contiguous range of slices carries the same mix of long and short rows.
-// Per order: sell_spmv_kernel (persistent, one CTA per SM, entries split evenly
-// over CTAs) writes one partial sum per virtual row into a row-major array;
-// sell_epilogue_kernel adds each row's partials in a fixed order
-// (deterministic), applies the Laplacian scaling, the three-term recurrence and
-// the scale accumulation.
+//     block are stored longest first: the hot kernel hands them out dynamically,
+//     so the short ones at the end of a block's queue keep the tail short.
+// This file: the plan build and the gather primitives.  The hot kernel
+// (sell_step.cuh) runs all orders of a step in one persistent launch: every CTA
+// serves one column block, warps pull slices from a per-block counter, one
+// partial sum per virtual row goes to a row-major array, and after a grid
+// barrier the same kernel adds each row's partials in a fixed order
+// (deterministic) and applies the Laplacian scaling, the three-term recurrence
+// and the scale accumulation.
 #pragma once
 
 #include <cub/device/device_radix_sort.cuh>
@@ -39,6 +41,9 @@
 namespace egnn {
 
 constexpr int kSellThreads = 1024;
+constexpr int kSellThreadsPerCta = kSellThreads;
+constexpr int kSellCtrStride = 32;        // one 128-byte line per column block's slice counter
+constexpr int kSellSchedWords = 64 * kSellCtrStride + 64;   // counters, then the grid-barrier counter
 constexpr int kSellSliceRows = 32;
 constexpr int kSellGroup = 8;           // indices per 16-byte load
 constexpr int kSellMaxBlocks = 64;
@@ -107,15 +112,9 @@ sell_emit_kernel(int n, int C, int lmax, const int32_t* __restrict__ seg_start,
 }
 
 // ---- build pass 3: block pointers (padded to whole slices) ------------------
-// Slices of a block are stored in a strided order of their length rank (slice
-// t holds the rows of rank (t * stride) mod n_c, stride ~ 0.618 n_c, coprime to
-// n_c): any contiguous range of slices - what one CTA of the hot kernel gets -
-// then carries the same mix of long and short rows, so equal entries mean equal time.
-__device__ __forceinline__ int sell_gcd(int a, int b) {
-    while (b) { const int t = a % b; a = b; b = t; }
-    return a;
-}
-
+// Slices of a block are stored in the order of their length rank (longest
+// first); blk_stride stays in the layout as a coprime multiplier of the rank
+// (1 now; a golden-ratio stride served the earlier static split of slices).
 __global__ void sell_blocks_kernel(int n, int C, const int32_t* __restrict__ u_off,
                                    int32_t* __restrict__ q_ptr, int32_t* __restrict__ vp_ptr,
                                    int32_t* __restrict__ blk_slice_ptr, int32_t* __restrict__ blk_stride,
@@ -129,10 +128,7 @@ __global__ void sell_blocks_kernel(int n, int C, const int32_t* __restrict__ u_o
         vp_ptr[c] = vp;
         blk_slice_ptr[c] = vp / kSellSliceRows;
         const int n_c = (q1 - q0 + kSellSliceRows - 1) / kSellSliceRows;
-        int stride = (int)(0.6180339887 * (double)n_c);
-        if (stride < 1) stride = 1;
-        while (sell_gcd(stride, n_c > 0 ? n_c : 1) != 1) ++stride;
-        blk_stride[c] = stride;
+        blk_stride[c] = 1;
         vp += n_c * kSellSliceRows;
     }
     q_ptr[C] = u_off[(size_t)C * n];
@@ -169,24 +165,55 @@ sell_slice_kernel(int C, int lmax, const uint32_t* __restrict__ key_sorted,
     slice_sz[s] = (len + kSellGroup - 1) / kSellGroup * kSellGroup * kSellSliceRows;
 }
 
-// CTA g of the hot kernel handles slices [cta_ptr[g], cta_ptr[g+1]): an even
-// split of the padded entries on slice boundaries, computed once per plan (in
-// the hot kernel the two binary searches were ~30 dependent loads per CTA).
-// cta_ptr[n_cta + 1 + g] = column block of that CTA's first slice.
-__global__ void sell_cta_ranges_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ blk_slice_ptr,
-                                       int C, int n_slices, int n_cta, int32_t* __restrict__ cta_ptr) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g > n_cta) return;
-    if (g == n_cta) { cta_ptr[g] = n_slices; cta_ptr[n_cta + 1 + g] = C; return; }
-    const int64_t total = slice_off[n_slices];
-    const int64_t want = total * g / n_cta;
-    int lo = 0, hi = n_slices;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((int64_t)slice_off[mid] < want) lo = mid + 1; else hi = mid;
+// Which column block every CTA of the hot kernel serves: CTAs are dealt to the
+// blocks in proportion to their padded entries (largest remainder; every
+// non-empty block gets at least one), so a CTA stages ONE operand block per
+// order and the CTAs of a block share its slices dynamically.
+// cta_info: [n_cta] block (-1: none), [n_cta] rank of the CTA inside its block,
+// [kSellMaxBlocks] start value of the block's slice counter (32 x its CTAs: the
+// first slice of every warp is fixed).  sched: the counters themselves + the
+// grid-barrier counter, initialised here.
+__global__ void sell_cta_blocks_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ blk_slice_ptr,
+                                       int C, int n_cta, int32_t* __restrict__ cta_info, unsigned* __restrict__ sched) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double w[kSellMaxBlocks], total = 0.0;
+    int cnt[kSellMaxBlocks];
+    for (int c = 0; c < C; ++c) {
+        w[c] = (double)(slice_off[blk_slice_ptr[c + 1]] - slice_off[blk_slice_ptr[c]]);
+        total += w[c];
     }
-    cta_ptr[g] = lo;
-    cta_ptr[n_cta + 1 + g] = sell_block_of_slice(blk_slice_ptr, C, lo);
+    int used = 0;
+    for (int c = 0; c < C; ++c) {
+        cnt[c] = w[c] > 0 ? max(1, (int)(w[c] / total * n_cta)) : 0;
+        used += cnt[c];
+    }
+    while (used > n_cta) {                           // more non-empty blocks' minimums than CTAs can not happen (C <= 64 < SMs)
+        int big = 0;
+        for (int c = 1; c < C; ++c) if (cnt[c] > cnt[big]) big = c;
+        --cnt[big]; --used;
+    }
+    while (used < n_cta && total > 0) {              // leftover CTAs go where the load per CTA is highest
+        int best = -1;
+        double best_load = 0.0;
+        for (int c = 0; c < C; ++c)
+            if (cnt[c] > 0 && w[c] / cnt[c] > best_load) { best_load = w[c] / cnt[c]; best = c; }
+        if (best < 0) break;
+        ++cnt[best]; ++used;
+    }
+    // CTAs of a block are interleaved with the other blocks' (block ids cycle over the grid), so
+    // every block's share of the SMs is spread over the whole chip
+    int g = 0, max_cnt = 0;
+    for (int c = 0; c < C; ++c) max_cnt = max(max_cnt, cnt[c]);
+    for (int r = 0; r < max_cnt; ++r)
+        for (int c = 0; c < C; ++c)
+            if (r < cnt[c]) { cta_info[g] = c; cta_info[n_cta + g] = r; ++g; }
+    for (; g < n_cta; ++g) { cta_info[g] = -1; cta_info[n_cta + g] = 0; }
+    for (int i = 0; i < kSellSchedWords; ++i) sched[i] = 0u;
+    for (int c = 0; c < kSellMaxBlocks; ++c) {
+        const int start = c < C ? cnt[c] * (kSellThreadsPerCta / 32) : 0;
+        cta_info[2 * n_cta + c] = start;
+        sched[c * kSellCtrStride] = (unsigned)start;
+    }
 }
 
 __global__ void sell_totals_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ rv_ptr,
@@ -315,10 +342,9 @@ sell_fill_kernel(const int32_t* __restrict__ colidx, int C, int CB, int lmax, in
     }
 }
 
-// ---- hot kernel ---------------------------------------------------------------
-// y: the gather operand dinv (.) T_{k-1}, [n] float32.  The partial sum of
-// virtual row v goes to vpart[vslot[v]] (row-major: a row's partials are
-// contiguous for the epilogue).  Dynamic shared memory: (CB + 32) floats.
+// ---- gather primitives of the hot kernel (sell_step.cuh) -----------------------
+// The partial sum of virtual row v goes to vpart[vslot[v]] (row-major: a row's
+// partials are contiguous for the epilogue).  Shared memory: (CB + 32) floats.
 __device__ __forceinline__ uint4 ld_stream_u32x4(const uint4* p) {
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -336,187 +362,5 @@ __device__ __forceinline__ float sell_gather8(const float* ysm, const uint4 q) {
 
 constexpr int kSellZeroSlots = 32;
 constexpr int kSellUnroll = 8;            // 16-byte index loads in flight per lane (measured best of 2/4/6/8)
-
-// PEER: the operand lives in this rank's exchange window and is written by the
-// other GPUs over NVLink; the CTA first waits for their flags, and stages with
-// L2-coherent loads (ld.global.cg) instead of the non-coherent path.
-struct SellPeerWait {
-    const unsigned* local_flags;
-    const unsigned* epoch;
-    unsigned* error;
-    int32_t world, rank;
-};
-
-template <int UNROLL, bool PEER>
-__global__ void __launch_bounds__(kSellThreads, 1)
-sell_spmv_kernel(const uint16_t* __restrict__ idx, const int32_t* __restrict__ slice_off,
-                 const int32_t* __restrict__ blk_slice_ptr, const int32_t* __restrict__ vslot,
-                 const int32_t* __restrict__ cta_ptr, int n_cta, int C, int CB, const float* y, int n,
-                 float* __restrict__ vpart, const SellPeerWait pw) {
-    extern __shared__ __align__(16) float ysm[];
-    __shared__ int next_slice;
-    __shared__ int bsp[kSellMaxBlocks + 1];
-    const int lane = threadIdx.x & 31;
-    const int wid = threadIdx.x >> 5;
-    constexpr int kWarps = kSellThreads / 32;
-
-    // everything that does not depend on the operand is requested first: this CTA's slice
-    // range and first column block (precomputed per plan), the block pointers, and - below -
-    // the index groups of every warp's first slice, which then fly during the flag wait
-    // (row-sharded) and the staging of the operand
-    const int s_begin = __ldg(cta_ptr + blockIdx.x), s_end = __ldg(cta_ptr + blockIdx.x + 1);
-    const int c_first = __ldg(cta_ptr + n_cta + 1 + blockIdx.x);
-    if (threadIdx.x <= C) bsp[threadIdx.x] = __ldg(blk_slice_ptr + threadIdx.x);
-    __syncthreads();
-
-    bool waited = !PEER;
-    for (int c = c_first; c < C; ++c) {
-        const int sub_begin = max(s_begin, bsp[c]);
-        const int sub_end = min(s_end, bsp[c + 1]);
-        if (sub_begin >= s_end) break;
-        if (sub_begin >= sub_end) continue;
-
-        // this warp's first slice of the block is fixed (sub_begin + warp id); the rest are
-        // handed out dynamically from a shared counter
-        int s = sub_begin + wid;
-        int off = 0, end = 0, slot = -1;
-        if (s < sub_end) {
-            off = __ldg(slice_off + s);
-            end = __ldg(slice_off + s + 1);
-            slot = __ldg(vslot + (size_t)s * kSellSliceRows + lane);
-        }
-        // ask L2 for the head of that slice's index stream (one 128-byte line per lane, no registers held)
-        if (s < sub_end) {
-            const char* head = reinterpret_cast<const char*>(idx + off) + lane * 128;
-            if (head < reinterpret_cast<const char*>(idx + end)) asm volatile("prefetch.global.L2 [%0];" ::"l"(head));
-        }
-        if (!waited) {                                     // operand written by the other GPUs: wait for their flags
-            peer_consumer_wait(pw.local_flags, pw.epoch, pw.world, pw.rank, pw.error);
-            waited = true;
-        }
-        __syncthreads();                                   // previous block's gathers are done
-        // stage the column block of the operand in shared memory
-        const int col0 = c * CB;
-        const int cnt = min(CB, n - col0);
-        const float* src = y + col0;
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-            const int cnt4 = cnt >> 2;
-            const float4* src4 = reinterpret_cast<const float4*>(src);
-            float4* dst4 = reinterpret_cast<float4*>(ysm);
-            for (int t = threadIdx.x; t < cnt4; t += kSellThreads) dst4[t] = PEER ? __ldcg(src4 + t) : __ldg(src4 + t);
-            for (int t = (cnt4 << 2) + threadIdx.x; t < cnt; t += kSellThreads) ysm[t] = PEER ? __ldcg(src + t) : __ldg(src + t);
-        } else {
-            for (int t = threadIdx.x; t < cnt; t += kSellThreads) ysm[t] = PEER ? __ldcg(src + t) : __ldg(src + t);
-        }
-        for (int t = cnt + threadIdx.x; t < CB + kSellZeroSlots; t += kSellThreads) ysm[t] = 0.f;   // includes the zero slots
-        if (threadIdx.x == 0) next_slice = sub_begin + kWarps;
-        __syncthreads();
-
-        while (s < sub_end) {
-            // the NEXT slice's offsets and slot are fetched while this one is summed
-            int s_next = 0;
-            if (lane == 0) s_next = atomicAdd(&next_slice, 1);
-            s_next = __shfl_sync(0xffffffffu, s_next, 0);
-            int off_next = 0, end_next = 0, slot_next = -1;
-            if (s_next < sub_end) {
-                off_next = __ldg(slice_off + s_next);
-                end_next = __ldg(slice_off + s_next + 1);
-                slot_next = __ldg(vslot + (size_t)s_next * kSellSliceRows + lane);
-            }
-            const int groups = (end - off) / (kSellGroup * kSellSliceRows);
-            const uint4* p = reinterpret_cast<const uint4*>(idx + off) + lane;
-            float acc0 = 0.f, acc1 = 0.f;
-            int g = 0;
-            for (; g + UNROLL <= groups; g += UNROLL) {
-                uint4 q[UNROLL];
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) q[u] = ld_stream_u32x4(p + (size_t)(g + u) * kSellSliceRows);
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    if (u & 1) acc1 += sell_gather8(ysm, q[u]);
-                    else acc0 += sell_gather8(ysm, q[u]);
-                }
-            }
-            for (; g < groups; ++g) acc0 += sell_gather8(ysm, ld_stream_u32x4(p + (size_t)g * kSellSliceRows));
-            if (slot >= 0) vpart[slot] = acc0 + acc1;
-            s = s_next; off = off_next; end = end_next; slot = slot_next;
-        }
-    }
-    if (!waited) peer_consumer_wait(pw.local_flags, pw.epoch, pw.world, pw.rank, pw.error);   // CTA without slices
-}
-
-// ---- per-row epilogue -----------------------------------------------------------
-struct SellEpilogueParams {
-    const int32_t* rv_ptr;
-    const float* vpart;      // row-major partial sums: row i owns [rv_ptr[i], rv_ptr[i+1])
-    const float* y_prev;     // gather operand (for the edge flips)
-    const float* dinv;
-    const uint8_t* iso;
-    const float* tprev;
-    const float* tprev2;     // may alias tk
-    float* tk;               // or NULL
-    float* y_out;            // or NULL
-    float* out;              // [n, S]
-    int32_t n, S, first, normalize;   // n: rows of this launch
-    int32_t row0;                     // global id of local row 0 (dinv/iso/deltas are global)
-    float a, b;
-    float c_prev[EGNN_MAX_SCALES];
-    float c_k[EGNN_MAX_SCALES];
-    DeltaList delta;
-    PeerPush peer;           // world > 1: dinv (.) T_k goes into every rank's exchange window
-};
-
-__device__ __forceinline__ void sell_epilogue_row(const SellEpilogueParams& p, int i) {
-    // everything that does not depend on the partial sums is requested first, so the row pays
-    // two dependent round trips (row pointers -> partials) instead of three
-    const int e = __ldg(p.rv_ptr + i + 1);
-    int t = __ldg(p.rv_ptr + i);
-    const float di = __ldg(p.dinv + p.row0 + i);
-    const float theta = fmaf(p.a, 1.f - (float)__ldg(p.iso + p.row0 + i), p.b);
-    float xprev = 0.f;
-    if (theta != 0.f || p.first) xprev = p.tprev[i];
-    const float t2 = p.first ? 0.f : p.tprev2[i];
-    float prev_out = 0.f;
-    if (!p.first && p.S == 1) prev_out = p.out[i];
-    // a hub row owns hundreds of virtual rows: add their partials in float64,
-    // always in the same order (deterministic)
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;          // four interleaved chains, always combined the same way
-    for (; t + 4 <= e; t += 4) {
-        a0 += (double)p.vpart[t];
-        a1 += (double)p.vpart[t + 1];
-        a2 += (double)p.vpart[t + 2];
-        a3 += (double)p.vpart[t + 3];
-    }
-    for (; t < e; ++t) a0 += (double)p.vpart[t];
-    double accd = (a0 + a1) + (a2 + a3);
-    for (int d = 0; d < p.delta.n; ++d)
-        if (p.delta.row[d] == i + p.row0 && p.delta.col[d] != i + p.row0)
-            accd += (double)p.delta.val[d] * (double)__ldg(p.y_prev + p.delta.col[d]);
-    const float acc = (float)accd;
-    const float lap = fmaf(theta, xprev, -p.a * di * acc);
-    const float tk = p.first ? lap : fmaf(2.f, lap, -t2);
-    if (p.tk) p.tk[i] = tk;
-    if (p.y_out) p.y_out[i] = di * tk;
-    if (p.peer.world > 1 && p.peer.has_data) {
-        const float yv = di * tk;
-        for (int r = 0; r < p.peer.world; ++r) p.peer.dst[r][p.row0 + i] = yv;
-    }
-    for (int s = 0; s < p.S; ++s) {
-        float o = p.first ? fmaf(p.c_k[s], tk, p.c_prev[s] * xprev)
-                          : fmaf(p.c_k[s], tk, p.S == 1 ? prev_out : p.out[(size_t)i * p.S + s]);
-        if (p.normalize) o = o / (fabsf(o) + 1e-8f);
-        p.out[(size_t)i * p.S + s] = o;
-    }
-}
-
-// Launched with one row per thread (256-thread CTAs) on a single GPU; with the exchange
-// fused it runs as at most one 1024-thread CTA per SM striding over the rows, because every
-// CTA ends with a system-scope fence and those serialise per SM (8 CTAs per SM measured
-// ~8 us of fences per order, one CTA per SM ~3 us).
-__global__ void __launch_bounds__(1024)
-sell_epilogue_kernel(const __grid_constant__ SellEpilogueParams p) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) sell_epilogue_row(p, i);
-    peer_producer_signal(p.peer);
-}
 
 }  // namespace egnn

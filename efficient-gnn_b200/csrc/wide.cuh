@@ -82,10 +82,26 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// PEER: the operand lives in this rank's exchange window and other GPUs write it while this
+// kernel is resident (before its flag wait), so the non-coherent path (.nc: read-only for the
+// kernel's lifetime) is not allowed; plain loads, ordered after the wait's fence.sys, are.
+template <bool PEER>
 __device__ __forceinline__ float4 ld_gather_f4(const float* p, uint64_t pol) {
     float4 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    if (PEER)
+        asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol) : "memory");
+    else
+        asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+template <bool PEER>
+__device__ __forceinline__ float4 ld_operand_f4(const float* p) {
+    if (!PEER) return __ldg(reinterpret_cast<const float4*>(p));
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ float4 ld_stream_f4(const float* p, uint64_t pol) {
@@ -123,7 +139,7 @@ __device__ __forceinline__ void store_user4(float* base, int64_t off, int ncol, 
 
 // Fused epilogue of one row tile; `writer` lanes (entry slot 0, column inside
 // the padded row) hold the row's sum in acc.  ncol = valid user columns of the lane.
-template <bool ALIGNED>
+template <bool ALIGNED, bool PEER>
 __device__ __forceinline__ void wide_epilogue(const WideParams& p, int row, int grow, int FL, int fcol, int ncol,
                                               bool writer, float (&acc)[4], uint64_t pol_stream, bool have_own,
                                               const float (&own)[4]) {
@@ -136,7 +152,7 @@ __device__ __forceinline__ void wide_epilogue(const WideParams& p, int row, int 
     if (p.delta.n > 0 && writer) {          // edge flips on top of the CSR (UGCA recompute)
         for (int e = 0; e < p.delta.n; ++e) {
             if (p.delta.row[e] == grow && p.delta.col[e] != grow) {
-                const float4 x = __ldg(reinterpret_cast<const float4*>(p.ysrc + (int64_t)p.delta.col[e] * ldy + fcol));
+                const float4 x = ld_operand_f4<PEER>(p.ysrc + (int64_t)p.delta.col[e] * ldy + fcol);
                 const float w = p.delta.val[e];
                 acc[0] = fmaf(w, x.x, acc[0]); acc[1] = fmaf(w, x.y, acc[1]);
                 acc[2] = fmaf(w, x.z, acc[2]); acc[3] = fmaf(w, x.w, acc[3]);
@@ -157,7 +173,7 @@ __device__ __forceinline__ void wide_epilogue(const WideParams& p, int row, int 
                 load_user4<ALIGNED>(p.x0_own, uoff, ncol, pol_stream, xprev);
             }
         } else if (theta != 0.f) {                              // T_{k-1} of the own row = y / dinv
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.ysrc + (int64_t)grow * ldy + fcol));
+            const float4 t = ld_operand_f4<PEER>(p.ysrc + (int64_t)grow * ldy + fcol);
             xprev[0] = t.x * inv_di; xprev[1] = t.y * inv_di; xprev[2] = t.z * inv_di; xprev[3] = t.w * inv_di;
         }
         float t2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -216,7 +232,7 @@ __device__ __forceinline__ void wide_epilogue(const WideParams& p, int row, int 
 // (pre_c, pre_w) when have_pre.  Full groups of UNR entries per slot run
 // branch-free; only the tail is guarded.  Two-level float32 summation: acc is
 // folded into hi every 64 entries of a chain.
-template <int NZ_LOG2, bool HAS_VALS>
+template <int NZ_LOG2, bool HAS_VALS, bool PEER>
 __device__ __forceinline__ void wide_accumulate(const WideParams& p, int qs, int qe, int grow, int lane, int nzl,
                                                 const float* ycol, bool have_pre, int pre_c, float pre_w,
                                                 uint64_t pol_keep, float (&sum)[4]) {
@@ -245,7 +261,7 @@ __device__ __forceinline__ void wide_accumulate(const WideParams& p, int qs, int
 #pragma unroll
             for (int j = 0; j < UNR; ++j) {
                 const int c = __shfl_sync(0xffffffffu, cj, e0 + j * NZ + nzl);
-                x[j] = ld_gather_f4(ycol + c * ldy, pol_keep);
+                x[j] = ld_gather_f4<PEER>(ycol + c * ldy, pol_keep);
             }
 #pragma unroll
             for (int j = 0; j < UNR; ++j) {
@@ -260,7 +276,7 @@ __device__ __forceinline__ void wide_accumulate(const WideParams& p, int qs, int
             for (int j = 0; j < UNR; ++j) {
                 if (e0 + j * NZ < cnt) {               // warp-uniform
                     const int c = __shfl_sync(0xffffffffu, cj, (e0 + j * NZ + nzl) & 31);
-                    x[j] = ld_gather_f4(ycol + c * ldy, pol_keep);
+                    x[j] = ld_gather_f4<PEER>(ycol + c * ldy, pol_keep);
                 }
             }
 #pragma unroll
@@ -283,7 +299,7 @@ __device__ __forceinline__ void wide_accumulate(const WideParams& p, int qs, int
     for (int v = 0; v < 4; ++v) sum[v] = hi[v] + acc[v];
 }
 
-template <int NZ_LOG2, bool HAS_VALS, bool ALIGNED>
+template <int NZ_LOG2, bool HAS_VALS, bool ALIGNED, bool PEER>
 __global__ void __launch_bounds__(kWideBlock, kWideMinBlocks)
 cheb_wide_kernel(const __grid_constant__ WideParams p) {
     __shared__ float hub_part[kWideWarps][128];
@@ -307,7 +323,7 @@ cheb_wide_kernel(const __grid_constant__ WideParams p) {
     const bool writer = nzl == 0 && col_ok;
     const float none[4] = {0.f, 0.f, 0.f, 0.f};
     // row-sharded: the operand sits in this rank's exchange window and the other GPUs fill it
-    peer_consumer_wait(p.peer.local_flags, p.peer.epoch, p.peer.world, p.peer.rank, p.peer.error);
+    if (PEER) peer_consumer_wait(p.peer.local_flags, p.peer.epoch, p.peer.world, p.peer.rank, p.peer.error);
 
     // ---- phase A: hub rows, one CTA each, longest first ---------------------
     for (int h = blockIdx.x; h < n_hub; h += gridDim.x) {
@@ -320,7 +336,7 @@ cheb_wide_kernel(const __grid_constant__ WideParams p) {
         const int qs = min(end, start + wid * per_warp * 32);
         const int qe = min(end, qs + per_warp * 32);
         float part[4];
-        wide_accumulate<NZ_LOG2, HAS_VALS>(p, qs, qe, grow, lane, nzl, ycol, false, 0, 0.f, pol_keep, part);
+        wide_accumulate<NZ_LOG2, HAS_VALS, PEER>(p, qs, qe, grow, lane, nzl, ycol, false, 0, 0.f, pol_keep, part);
 #pragma unroll
         for (int o = FL; o < 32; o <<= 1) {
 #pragma unroll
@@ -340,7 +356,7 @@ cheb_wide_kernel(const __grid_constant__ WideParams p) {
                 for (int w = 0; w < kWideWarps; ++w) t += hub_part[w][fl * 4 + v];     // fixed order
                 acc[v] = t;
             }
-            wide_epilogue<ALIGNED>(p, row, grow, FL, fcol, ncol, writer, acc, pol_stream, false, none);
+            wide_epilogue<ALIGNED, PEER>(p, row, grow, FL, fcol, ncol, writer, acc, pol_stream, false, none);
         }
     }
 
@@ -381,7 +397,7 @@ cheb_wide_kernel(const __grid_constant__ WideParams p) {
         }
         const int grow = (int)p.row0 + row;
         float acc[4];
-        wide_accumulate<NZ_LOG2, HAS_VALS>(p, start, end, grow, lane, nzl, ycol, true, pre_c, pre_w, pol_keep, acc);
+        wide_accumulate<NZ_LOG2, HAS_VALS, PEER>(p, start, end, grow, lane, nzl, ycol, true, pre_c, pre_w, pol_keep, acc);
         int pre_c_n = 0;
         float pre_w_n = 0.f;
         float own_n[4] = {0.f, 0.f, 0.f, 0.f};
@@ -397,12 +413,12 @@ cheb_wide_kernel(const __grid_constant__ WideParams p) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], o);
         }
-        wide_epilogue<ALIGNED>(p, row, grow, FL, fcol, ncol, writer, acc, pol_stream, have_own, own);
+        wide_epilogue<ALIGNED, PEER>(p, row, grow, FL, fcol, ncol, writer, acc, pol_stream, have_own, own);
         r = r_next; row = row_n; start = start_n; end = end_n; pre_c = pre_c_n; pre_w = pre_w_n;
 #pragma unroll
         for (int v = 0; v < 4; ++v) own[v] = own_n[v];
     }
-    peer_producer_signal(p.peer);
+    if (PEER) peer_producer_signal(p.peer);
 }
 
 // ---- pre-scaled copy of the input signal into a padded slab ---------------------

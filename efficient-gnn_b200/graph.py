@@ -17,7 +17,7 @@ import torch
 
 from . import _cabi
 
-__all__ = ["CsrGraph", "as_graph"]
+__all__ = ["CsrGraph", "as_graph", "enable_phase_stamps", "read_phase_stamps"]
 
 
 def _stream():
@@ -149,7 +149,7 @@ class CsrGraph:
     @classmethod
     def from_scipy(cls, mat, device="cuda") -> "CsrGraph":
         import scipy.sparse as sp
-        m = sp.csr_matrix(mat)
+        m = sp.csr_matrix(mat, copy=True)      # never canonicalise the caller's arrays in place
         m.sum_duplicates()
         m.eliminate_zeros()
         m.sort_indices()
@@ -192,6 +192,7 @@ class CsrGraph:
             self._colsum = torch.empty(n, dtype=torch.float64, device=dev)
             self._unsorted_flag = torch.empty(1, dtype=torch.int32, device=dev)
         self._sell = None          # lazily built SELL plan (False: not applicable)
+        self._sell_structural = False   # the False above is final (weighted / unsorted / empty), not a threshold
         self.narrow_calls = 0      # F = 1 passes run on this graph (the plan is built on the second)
         self._row_order = None     # lazily built processing order of the wide kernel
 
@@ -236,19 +237,22 @@ class CsrGraph:
         (include/egnn_b200.h ``egnn_sell_plan``), built once per graph on the
         device.  Returns ``None`` when the graph does not qualify (weighted,
         unsorted rows, small or very sparse): the generic CSR kernel serves it."""
-        if self._sell is not None:
+        if self._sell is not None and (self._sell or not force or self._sell_structural):
             return self._sell or None
+        # structural disqualifiers are final; the size / density thresholds are re-evaluated under force
         self._sell = False
+        self._sell_structural = True
         if self.vals is not None or self.n < 1 or self.nnz == 0:
             return None
+        if bool(self._unsorted_flag.item()):
+            return None
+        self._sell_structural = False
         lib = _cabi.load()
         nb, cb, lmax = C.c_int32(0), C.c_int32(0), C.c_int32(0)
         _cabi.check(lib.egnn_sell_geometry(self.n, self.nnz, C.byref(nb), C.byref(cb), C.byref(lmax)),
                     "egnn_sell_geometry")
         if not force and (self.nnz < self.SELL_MIN_NNZ or
                           self.nnz / (self.n * nb.value) < self.SELL_MIN_SEGMENT):
-            return None
-        if bool(self._unsorted_flag.item()):
             return None
         plan = build_sell_plan(self.rowptr, self.colidx, self.n, self.n, 0, (nb.value, cb.value, lmax.value))
         self._sell = plan
@@ -270,7 +274,7 @@ class CsrGraph:
                 _cabi.host_array(C.c_int32, [int(v) for v in delta_rows]),
                 _cabi.host_array(C.c_int32, [int(v) for v in delta_cols]),
                 _cabi.host_array(C.c_float, [float(v) for v in delta_vals]), nd,
-                _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(x0), _stream()), "egnn_patch_degrees")
+                _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(x0), 0, n, _stream()), "egnn_patch_degrees")
         return dinv, iso, x0
 
     def to_scipy(self):
@@ -304,8 +308,9 @@ def build_sell_plan(rowptr: torch.Tensor, colidx: torch.Tensor, n_rows: int, n_c
             "idx": torch.empty(max(1, plan.n_entries), dtype=torch.int16, device=dev),
             "rv_ptr": torch.empty(n_rows + 1, dtype=torch.int32, device=dev),
             "vslot": torch.empty(max(1, plan.n_vrows), dtype=torch.int32, device=dev),
-            "cta_ptr": torch.empty(2 * (plan.n_cta + 1), dtype=torch.int32, device=dev),
+            "cta_info": torch.empty(2 * plan.n_cta + 64, dtype=torch.int32, device=dev),
             "vpart": torch.empty(max(1, plan.n_rowv), dtype=torch.float32, device=dev),
+            "sched": torch.zeros(64 * 32 + 64, dtype=torch.int32, device=dev),
         }
         for name, t in bufs.items():
             setattr(plan, name, t.data_ptr())
@@ -313,6 +318,44 @@ def build_sell_plan(rowptr: torch.Tensor, colidx: torch.Tensor, n_rows: int, n_c
                                        C.byref(plan), _cabi.ptr(ws), ws_bytes, _stream()), "egnn_sell_fill")
     plan._keepalive = bufs
     return plan
+
+
+def enable_phase_stamps(plan, on: bool = True, trace: bool = False):
+    """Ask the step kernel to record CTA 0's ``globaltimer`` at kernel start,
+    after every grid barrier and at the end (``egnn_sell_plan.stamps``); read
+    them with :func:`read_phase_stamps`.  A measurement aid for bench.py."""
+    if on:
+        if "stamps" not in plan._keepalive:      # 64 global stamps + (trace) 64 per CTA
+            plan._keepalive["stamps"] = torch.zeros(64 + 64 * plan.n_cta, dtype=torch.int64,
+                                                    device=plan._keepalive["sched"].device)
+        plan.stamps = plan._keepalive["stamps"].data_ptr()
+        plan.reserved = 1 if trace else 0
+    else:
+        plan.stamps = None
+        plan.reserved = 0
+
+
+def read_phase_stamps(plan, k: int, first_operand_in_kernel: bool = True):
+    """Phase durations (microseconds) of the last step-kernel launch of ``k``
+    orders: ``{"prologue", "spmv": [...], "epilogue": [...], "total"}``.  The
+    SpMV figure of an order runs from the previous barrier to the barrier that
+    closes it (operand staging included); the epilogue of the last order ends
+    with the kernel."""
+    st = plan._keepalive["stamps"].cpu().numpy().astype("int64")
+    i = 0
+    t0 = st[i]; i += 1
+    res = {"prologue": 0.0, "spmv": [], "epilogue": []}
+    prev = t0
+    if first_operand_in_kernel:
+        res["prologue"] = (st[i] - prev) / 1e3
+        prev = st[i]; i += 1
+    for order in range(1, k + 1):
+        res["spmv"].append((st[i] - prev) / 1e3)
+        prev = st[i]; i += 1
+        res["epilogue"].append((st[i] - prev) / 1e3)       # barrier after the epilogue, or the end stamp for the last order
+        prev = st[i]; i += 1
+    res["total"] = (prev - t0) / 1e3
+    return res
 
 
 def as_graph(adj, device="cuda") -> CsrGraph:

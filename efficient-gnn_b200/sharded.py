@@ -77,6 +77,13 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _delta_args(deltas):
+    """(rows, cols, vals) -> the four delta arguments of the C ABI (host arrays + count)."""
+    d_rows, d_cols, d_vals = ([], [], []) if deltas is None else deltas
+    return (_cabi.host_array(C.c_int32, [int(v) for v in d_rows]), _cabi.host_array(C.c_int32, [int(v) for v in d_cols]),
+            _cabi.host_array(C.c_float, [float(v) for v in d_vals]), len(d_rows))
+
+
 class CudaEngine:
     """Device side of the sharded path: thin calls into libegnn_b200."""
 
@@ -98,20 +105,33 @@ class CudaEngine:
         iso = torch.empty(n_global, dtype=torch.uint8, device=dev)
         x0 = torch.empty(max(1, n_rows), dtype=torch.float32, device=dev)
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        w = torch.empty(n_global, dtype=torch.float32, device=dev)
         args = (_cabi.ptr(rowptr), _cabi.ptr(colidx), None, n_global, row_begin, n_rows)
         _cabi.check(lib.egnn_graph_prep_sharded(*args, 0, _cabi.ptr(colsum), _cabi.ptr(diag), _cabi.ptr(rowsum),
-                                                None, None, None, _cabi.ptr(flag), _stream()), "prep phase 0")
+                                                None, None, None, _cabi.ptr(flag), None, _stream()), "prep phase 0")
         allreduce(colsum)
         allreduce(diag)
         _cabi.check(lib.egnn_graph_prep_sharded(*args, 1, _cabi.ptr(colsum), _cabi.ptr(diag), _cabi.ptr(rowsum),
-                                                _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(x0), None, _stream()),
-                    "prep phase 1")
+                                                _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(x0), None, _cabi.ptr(w),
+                                                _stream()), "prep phase 1")
+        self.w_full, self.rowsum_local = w, rowsum[:n_rows]      # kept for the UGCA degree patches
         return dinv, iso, x0[:n_rows], bool(flag.item())
+
+    def patch_degrees(self, dinv, iso, x0_local, n_global, row_begin, n_rows, deltas):
+        """(dinv, iso, x0_local) of the graph with edge flips applied (global ids)."""
+        d_rows, d_cols, d_vals = deltas
+        dinv2, iso2 = torch.empty_like(dinv), torch.empty_like(iso)
+        x02 = torch.empty(max(1, n_rows), dtype=torch.float32, device=self.device)
+        _cabi.check(self.lib.egnn_patch_degrees(
+            _cabi.ptr(self.w_full), _cabi.ptr(self.rowsum_local), _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(x0_local),
+            n_global, *_delta_args(deltas), _cabi.ptr(dinv2), _cabi.ptr(iso2), _cabi.ptr(x02), row_begin, n_rows,
+            _stream()), "egnn_patch_degrees")
+        return dinv2, iso2, x02[:n_rows]
 
     # -- generic CSR kernel, one order ---------------------------------------
     def order(self, phase, local, remote, dinv, iso, t_prev_full, t_prev_local, t_prev2_local, t_out_local,
               out_local, acc_ws, n_global, nnz_hint, row_begin, row_end, f, order, k_max, n_scales, coeffs,
-              op_scale, op_shift, normalize):
+              op_scale, op_shift, normalize, deltas=None):
         lp, lc = (None, None) if local is None else local
         rp, rc = (None, None) if remote is None else remote
         _cabi.check(self.lib.egnn_cheb_order_sharded(
@@ -119,7 +139,7 @@ class CudaEngine:
             _cabi.ptr(t_prev_full), _cabi.ptr(t_prev_local), _cabi.ptr(t_prev2_local), _cabi.ptr(t_out_local),
             _cabi.ptr(out_local), _cabi.ptr(acc_ws), n_global, nnz_hint, row_begin, row_end, f, order, k_max,
             n_scales, coeffs.ctypes.data_as(C.c_void_p), float(op_scale), float(op_shift), 1 if normalize else 0,
-            phase, _stream()), "egnn_cheb_order_sharded")
+            phase, *_delta_args(deltas), _stream()), "egnn_cheb_order_sharded")
 
     # -- narrow path -----------------------------------------------------------
     def sell_plan(self, rowptr, colidx, n_rows, n_cols, row0, unsorted):
@@ -138,13 +158,18 @@ class CudaEngine:
         _cabi.check(self.lib.egnn_prescale(_cabi.ptr(x_local), _cabi.ptr(dinv), _cabi.ptr(y_local), n_rows, f, row0,
                                            _stream()), "egnn_prescale")
 
-    def sell_order(self, plan, y_full, dinv, iso, t_prev, t_prev2, t_out, y_out, out, order, k_max, n_scales,
-                   coeffs, op_scale, op_shift, normalize, window=None):
-        _cabi.check(self.lib.egnn_sell_order_sharded(
-            C.byref(plan), _cabi.ptr(y_full), _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(t_prev), _cabi.ptr(t_prev2),
-            _cabi.ptr(t_out), _cabi.ptr(y_out), _cabi.ptr(out), order, k_max, n_scales,
-            coeffs.ctypes.data_as(C.c_void_p), float(op_scale), float(op_shift), 1 if normalize else 0, _stream(),
-            None if window is None else C.byref(window)), "egnn_sell_order_sharded")
+    def sell_step(self, plan, dinv, iso, x0, y_first_full, y_slabs, tbufs, t_all, out, order_begin, order_end, k_max,
+                  n_scales, coeffs, op_scale, op_shift, normalize, deltas=None, window=None):
+        """Orders order_begin..order_end of the narrow path in one persistent launch
+        (include/egnn_b200.h ``egnn_sell_step_sharded``)."""
+        ys = (None, None) if y_slabs is None else y_slabs
+        tb = (None, None) if tbufs is None else tbufs
+        _cabi.check(self.lib.egnn_sell_step_sharded(
+            C.byref(plan), _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(x0), _cabi.ptr(y_first_full),
+            _cabi.ptr(ys[0]), _cabi.ptr(ys[1]), _cabi.ptr(tb[0]), _cabi.ptr(tb[1]), _cabi.ptr(t_all), _cabi.ptr(out),
+            order_begin, order_end, k_max, n_scales, coeffs.ctypes.data_as(C.c_void_p), float(op_scale),
+            float(op_shift), 1 if normalize else 0, *_delta_args(deltas),
+            None if window is None else C.byref(window), _stream()), "egnn_sell_step_sharded")
 
     def peer_prescale_push(self, x_local, dinv, n_rows, row0, f, window):
         _cabi.check(self.lib.egnn_peer_prescale_push(_cabi.ptr(x_local), _cabi.ptr(dinv), n_rows, row0, f,
@@ -160,12 +185,12 @@ class CudaEngine:
         return order
 
     def wide_order(self, rowptr, colidx, row_order, dinv, iso, x0_local, t_out, out, n_global, row_begin, row_end, f,
-                   order, k_max, n_scales, coeffs, op_scale, op_shift, normalize, window):
+                   order, k_max, n_scales, coeffs, op_scale, op_shift, normalize, window, deltas=None):
         _cabi.check(self.lib.egnn_wide_order_sharded(
             _cabi.ptr(rowptr), _cabi.ptr(colidx), None, _cabi.ptr(row_order), _cabi.ptr(dinv), _cabi.ptr(iso),
             _cabi.ptr(x0_local), _cabi.ptr(t_out), _cabi.ptr(out), n_global, row_begin, row_end, f, order, k_max,
             n_scales, coeffs.ctypes.data_as(C.c_void_p), float(op_scale), float(op_shift), 1 if normalize else 0,
-            C.byref(window), _stream()), "egnn_wide_order_sharded")
+            *_delta_args(deltas), C.byref(window), _stream()), "egnn_wide_order_sharded")
 
     # -- stream plumbing ---------------------------------------------------------
     def side_stream(self):
@@ -300,6 +325,14 @@ class ShardedWavelet:
         self.plan = None
         if use_sell is not False:
             self.plan = self.engine.sell_plan(self.rowptr, self.colidx, self.rows, self.n, self.row_begin, unsorted)
+        # The narrow path exchanges the PRE-SCALED operand dinv * T, the generic path plain T:
+        # every rank must run the same one.  A rank whose shard does not qualify for the plan
+        # (unsorted rows, too sparse, no rows) takes the plan away from all of them.
+        if self.world > 1:
+            have = torch.tensor([1.0 if self.plan is not None else 0.0], dtype=torch.float64, device=self.device)
+            self._allreduce(have)
+            if int(round(float(have.item()))) != self.world:
+                self.plan = None
         # Fused exchange over peer memory for the narrow path: needs real peers
         # (one process per GPU, NCCL group) and the plan on every rank.
         self.peer = None
@@ -322,13 +355,14 @@ class ShardedWavelet:
             self.peer, peer_exchange = peer_exchange, False
         if peer_exchange is None:
             peer_exchange = real_group and os.environ.get("EGNN_EXCHANGE", "peer") != "nccl"
+        self._owned_peers = []         # windows this instance allocated (closed by close(); borrowed ones are not)
+        self._lender = borrowed        # instance whose windows (and window table) this one shares
         if peer_exchange:
             if not real_group:
                 raise _cabi.EgnnError("peer exchange needs one process per GPU in an NCCL group")
-            have = torch.tensor([1 if self.plan is not None else 0], device=self.device)
-            dist.all_reduce(have, op=dist.ReduceOp.MIN, group=group)
-            if int(have.item()) == 1:
+            if self.plan is not None:      # agreed on by every rank above
                 self.peer = PeerExchange(self.part.rows_per, 1, group=group, device=self.device)
+                self._owned_peers.append(self.peer)
         self.fused_wide = borrowed.fused_wide if borrowed is not None else bool(real_group and peer_exchange)
         # default signal X0 = log1p(degree): every rank keeps the whole pre-scaled vector (one
         # all-gather at build time), so order 1 of the fused narrow path needs no exchange
@@ -346,6 +380,7 @@ class ShardedWavelet:
         """Exchange window for ``ldy``-wide operand rows (collective on first use)."""
         if ldy not in self._wide_peers:
             self._wide_peers[ldy] = PeerExchange(self.part.rows_per, ldy, group=self._group, device=self.device)
+            (self._lender or self)._owned_peers.append(self._wide_peers[ldy])
         return self._wide_peers[ldy]
 
     def exchange_error(self) -> int:
@@ -354,6 +389,26 @@ class ShardedWavelet:
         for px in self._wide_peers.values():
             err |= px.error()
         return err
+
+    def check_exchange(self):
+        """Raise when a flag wait of the fused exchange timed out (a peer never
+        signalled within the kernel's 30 s limit): the kernels keep running on
+        stale operands after a timeout, so results since the last check are not
+        to be trusted.  Synchronises the stream (one 4-byte D2H copy per window)."""
+        if self.exchange_error():
+            raise _cabi.EgnnError(f"rank {self.rank}: a peer-exchange flag wait timed out; features computed since "
+                                  "the last check used stale operands")
+
+    def close(self):
+        """Free the exchange windows this instance allocated (collective: every
+        rank calls it).  Windows borrowed from another instance stay open."""
+        owned, self._owned_peers = self._owned_peers, []
+        for px in owned:
+            px.close()
+        if self.peer in owned:
+            self.peer = None
+        for k in [k for k, v in self._wide_peers.items() if v in owned]:
+            del self._wide_peers[k]
 
     # -- collectives -------------------------------------------------------------
     def _allreduce(self, t):
@@ -364,15 +419,28 @@ class ShardedWavelet:
 
     # -- the path ------------------------------------------------------------------
     def features(self, k=3, s=0.8, *, X0_local=None, lambda_max: float = 2.0, normalize: bool = True,
-                 return_parts: bool = False):
+                 return_parts: bool = False, deltas=None):
         """Features of the local rows ``[rows, S*F]`` (reference defaults
         k=3, s=0.8, X0 = log1p(degree)); with ``return_parts`` also the local
-        slabs of every order and the un-normalised combination."""
+        slabs of every order and the un-normalised combination.
+
+        ``deltas=(rows, cols, vals)``: edge flips with GLOBAL node ids applied
+        on top of the sharded graph without rebuilding it - the UGCA
+        per-perturbation recompute (calib_attack/calib_fga.py:868,908,952) on a
+        graph that spans several GPUs.  Every rank passes the same list; each
+        patches its replicated dinv/iso and the x0 of its own rows, and the
+        order kernels add the flipped entries of the rows they own."""
         eng, dev = self.engine, self.device
         k = int(k)
         coeffs = np.ascontiguousarray(heat_coefficients(k, s), dtype=np.float32)
         n_scales = coeffs.shape[0]
-        x0 = self.x0.reshape(-1, 1) if X0_local is None else torch.as_tensor(X0_local)
+        dinv, iso, x0_default = self.dinv, self.iso, self.x0
+        if deltas is not None and len(deltas[0]) > 0:
+            dinv, iso, x0_default = eng.patch_degrees(self.dinv, self.iso, self.x0, self.n, self.row_begin, self.rows,
+                                                      deltas)
+        else:
+            deltas = None
+        x0 = x0_default.reshape(-1, 1) if X0_local is None else torch.as_tensor(X0_local)
         if x0.dim() == 1:
             x0 = x0.reshape(-1, 1)
         if x0.shape[0] != self.rows:
@@ -387,52 +455,88 @@ class ShardedWavelet:
             # rows beyond self.rows (short last shard) are exchanged but never read: no fill needed
             return torch.empty((rp, f), dtype=torch.float32, device=dev)
 
-        # order 1 writes every (row, scale, column) of out, so it is not cleared either
-        out = torch.empty((max(1, self.rows), n_scales, f), dtype=torch.float32, device=dev)
-        orders = [x0]
-        if k == 0:
-            out[:self.rows] = torch.from_numpy(coeffs[:, 0]).to(dev).reshape(1, -1, 1) * x0.unsqueeze(1)
-        use_plan = self.plan is not None and f == 1
-        fused = use_plan and self.peer is not None
-        fused_wide = self.fused_wide and f >= WIDE_MIN_F and k >= 1
-        if fused_wide:
-            # wide signal, exchange fused: operand rows live in the peers' windows (16-byte padded rows)
-            win = self._wide_window((f + 3) // 4 * 4).window
-            if self._row_order is None:
-                self._row_order = eng.row_order(self.rowptr, self.rows)
-            eng.peer_prescale_push(x0, self.dinv, self.rows, self.row_begin, f, win)
-            self.launches += 1
-            for order in range(1, k + 1):
-                t_out = torch.empty((self.rows, f), dtype=torch.float32, device=dev) if return_parts else None
-                eng.wide_order(self.rowptr, self.colidx, self._row_order, self.dinv, self.iso,
-                               x0 if order == 1 else None, t_out, out, self.n, self.row_begin, self.row_end, f, order,
-                               k, n_scales, coeffs, op_scale, op_shift, fused_norm, win)
-                self.launches += 1
-                if return_parts:
-                    orders.append(t_out)
+        def finish(out, orders):
             out = out[:self.rows]
+            if k == 0 and fused_norm:
+                out = out / (out.abs().sum(dim=2, keepdim=True) + 1e-8)
             if return_parts:
                 comb = out
                 feats = comb / (comb.abs().sum(dim=2, keepdim=True) + 1e-8) if normalize else comb
                 return feats.reshape(self.rows, -1), orders, comb
             return out.reshape(self.rows, -1)
-        if fused or self.rows == rp:
-            t_prev = x0                       # no exchange of T_0 itself, or already slab-sized
+
+        # order 1 writes every (row, scale, column) of out, so it is not cleared either
+        out = torch.empty((max(1, self.rows), n_scales, f), dtype=torch.float32, device=dev)
+        orders = [x0]
+        if k == 0:
+            out[:self.rows] = torch.from_numpy(coeffs[:, 0]).to(dev).reshape(1, -1, 1) * x0.unsqueeze(1)
+            return finish(out, orders)
+        use_plan = self.plan is not None and f == 1
+        fused = use_plan and self.peer is not None
+        fused_wide = self.fused_wide and f >= WIDE_MIN_F
+        if fused_wide:
+            # wide signal, exchange fused: operand rows live in the peers' windows (16-byte padded rows)
+            win = self._wide_window((f + 3) // 4 * 4).window
+            if self._row_order is None:
+                self._row_order = eng.row_order(self.rowptr, self.rows)
+            eng.peer_prescale_push(x0, dinv, self.rows, self.row_begin, f, win)
+            self.launches += 1
+            for order in range(1, k + 1):
+                t_out = torch.empty((self.rows, f), dtype=torch.float32, device=dev) if return_parts else None
+                eng.wide_order(self.rowptr, self.colidx, self._row_order, dinv, iso,
+                               x0 if order == 1 else None, t_out, out, self.n, self.row_begin, self.row_end, f, order,
+                               k, n_scales, coeffs, op_scale, op_shift, fused_norm, win, deltas)
+                self.launches += 1
+                if return_parts:
+                    orders.append(t_out)
+            return finish(out, orders)
+        if use_plan:
+            # narrow path: the persistent step kernel over the rank's SELL plan (csrc/sell_step.cuh)
+            rows1 = max(1, self.rows)
+            t_all = None
+            tbufs = None
+            if return_parts:
+                t_all = torch.empty((k + 1, rows1), dtype=torch.float32, device=dev)
+                t_all[0, :self.rows] = x0[:, 0]
+            elif k >= 2:
+                tbufs = (torch.empty(rows1, dtype=torch.float32, device=dev),
+                         torch.empty(rows1, dtype=torch.float32, device=dev))
+            tail = (k, n_scales, coeffs, op_scale, op_shift, fused_norm, deltas)
+            if fused:
+                # the whole step is ONE launch: operands travel through the exchange windows, the
+                # kernel waits on the owners' flags per column block and signals from its epilogue
+                y0 = self.y0_full if (X0_local is None and deltas is None) else None
+                eng.sell_step(self.plan, dinv, iso, x0, y0, None, tbufs, t_all, out, 1, k, *tail,
+                              window=self.peer.window)
+                self.launches += 1
+            elif self.world == 1:
+                y_slabs = (torch.empty(self.n, dtype=torch.float32, device=dev),
+                           torch.empty(self.n, dtype=torch.float32, device=dev))
+                eng.sell_step(self.plan, dinv, iso, x0, None, y_slabs, tbufs, t_all, out, 1, k, *tail)
+                self.launches += 1
+            else:
+                # collective exchange (NCCL all-gather or an injected comm): one launch per order
+                y_slabs = (slab(), slab())
+                full = torch.empty((self.world * rp, 1), dtype=torch.float32, device=dev)
+                if self.rows:
+                    eng.prescale(x0, dinv, y_slabs[0], self.rows, 1, self.row_begin)
+                for order in range(1, k + 1):
+                    self._allgather(full, y_slabs[(order - 1) & 1])
+                    if self.rows:
+                        eng.sell_step(self.plan, dinv, iso, x0, full, y_slabs, tbufs, t_all, out, order, order, *tail)
+                        self.launches += 1
+            if return_parts:
+                orders += [t_all[i, :self.rows].reshape(-1, 1) for i in range(1, k + 1)]
+            return finish(out, orders)
+        # generic CSR kernel, local / remote column halves around the exchange of T_{k-1}
+        if self.rows == rp:
+            t_prev = x0
         else:
             t_prev = slab()
             t_prev[:self.rows] = x0
         t_prev2 = None
-        full = None if fused else torch.empty((self.world * rp, f), dtype=torch.float32, device=dev)
-        y0_known = fused and X0_local is None and self.y0_full is not None
-        if fused and not y0_known:
-            eng.peer_prescale_push(t_prev, self.dinv, self.rows, self.row_begin, 1, self.peer.window)
-            self.launches += 1
-        elif use_plan:
-            y_slabs = [slab(), slab()]
-            if self.rows:
-                eng.prescale(t_prev, self.dinv, y_slabs[0], self.rows, f, self.row_begin)
-        else:
-            acc_ws = slab()
+        full = torch.empty((self.world * rp, f), dtype=torch.float32, device=dev)
+        acc_ws = slab()
         for order in range(1, k + 1):
             last = order == k
             if return_parts:
@@ -443,48 +547,31 @@ class ShardedWavelet:
                 t_out = slab()
             else:
                 t_out = t_prev2               # in place over T_{k-2} (read-then-write per element)
-            if fused:
-                # operand already sits in every rank's window; SpMV waits on flags, epilogue pushes the next one
-                eng.sell_order(self.plan, self.y0_full if (y0_known and order == 1) else None, self.dinv, self.iso,
-                               t_prev, t_prev2, t_out, None, out, order, k, n_scales, coeffs, op_scale, op_shift,
-                               fused_norm, window=self.peer.window)
+            # exchange T_{k-1} on the side stream while the local-column half runs
+            eng.fork()
+            with eng.side_stream():
+                self._allgather(full, t_prev)
+            common = (dinv, iso)
+            tail = (self.n, max(1, self.nnz_local), self.row_begin, self.row_end, f, order, k, n_scales, coeffs,
+                    op_scale, op_shift, fused_norm)
+            if self.rows:
+                eng.order(0, self.local_half, None, *common, None, t_prev, t_prev2, t_out, out, acc_ws, *tail)
+            eng.join()
+            if self.rows:
+                eng.order(1, None, self.remote_half, *common, full, t_prev, t_prev2, t_out, out, acc_ws, *tail,
+                          deltas=deltas)
                 self.launches += 2
-            elif use_plan:
-                y_prev = y_slabs[(order - 1) & 1]
-                self._allgather(full, y_prev)
-                if self.rows:
-                    eng.sell_order(self.plan, full, self.dinv, self.iso, t_prev, t_prev2, t_out,
-                                   None if last else y_slabs[order & 1], out, order, k, n_scales, coeffs,
-                                   op_scale, op_shift, fused_norm)
-                    self.launches += 2
-            else:
-                # exchange T_{k-1} on the side stream while the local-column half runs
-                eng.fork()
-                with eng.side_stream():
-                    self._allgather(full, t_prev)
-                common = (self.dinv, self.iso)
-                tail = (self.n, max(1, self.nnz_local), self.row_begin, self.row_end, f, order, k, n_scales, coeffs,
-                        op_scale, op_shift, fused_norm)
-                if self.rows:
-                    eng.order(0, self.local_half, None, *common, None, t_prev, t_prev2, t_out, out, acc_ws, *tail)
-                eng.join()
-                if self.rows:
-                    eng.order(1, None, self.remote_half, *common, full, t_prev, t_prev2, t_out, out, acc_ws, *tail)
-                    self.launches += 2
             if return_parts:
                 orders.append(t_out[:self.rows])
             t_prev2, t_prev = t_prev, t_out
-        out = out[:self.rows]
-        if k == 0 and fused_norm:
-            out = out / (out.abs().sum(dim=2, keepdim=True) + 1e-8)
-        if return_parts:
-            comb = out
-            feats = comb / (comb.abs().sum(dim=2, keepdim=True) + 1e-8) if normalize else comb
-            return feats.reshape(self.rows, -1), orders, comb
-        return out.reshape(self.rows, -1)
+        return finish(out, orders)
 
     def gather_features(self, local_feats):
-        """All ranks' feature rows, ``[N, S*F]`` on every rank."""
+        """All ranks' feature rows, ``[N, S*F]`` on every rank.  A natural
+        synchronisation point: the error words of the fused exchange are
+        checked here (:meth:`check_exchange`)."""
+        if self.peer is not None or self._wide_peers:
+            self.check_exchange()
         rp = self.part.rows_per
         pad = torch.zeros((rp, local_feats.shape[1]), dtype=local_feats.dtype, device=local_feats.device)
         pad[:self.rows] = local_feats

@@ -105,14 +105,18 @@ int egnn_graph_prep_finish(const double* colsum, const float* diag, const float*
  * the calibrated surrogate on a perturbed adjacency): copies dinv/iso/x0 of
  * the base graph into the *_out vectors and re-derives the entries of every
  * node an edge flip touches.  Flip e adds delta_val[e] to
- * A[delta_row[e], delta_col[e]] (host arrays, n_delta <= EGNN_MAX_DELTA).   */
+ * A[delta_row[e], delta_col[e]] (host arrays, n_delta <= EGNN_MAX_DELTA).
+ * w/dinv/iso are full-length [n]; rowsum_base/x0_base/x0_out hold the rows
+ * [row_begin, row_begin + n_rows) - the whole graph (0, n) on one GPU, the
+ * rank's rows on a row shard (flips are global ids; every rank patches its
+ * replicated dinv/iso and its own rows of x0).                               */
 int egnn_patch_degrees(const float* w_base, const float* rowsum_base,
                        const float* dinv_base, const uint8_t* iso_base,
                        const float* x0_base, int64_t n,
                        const int32_t* delta_row_host, const int32_t* delta_col_host,
                        const float* delta_val_host, int32_t n_delta,
                        float* dinv_out, uint8_t* iso_out, float* x0_out,
-                       egnn_stream_t stream);
+                       int64_t row_begin, int64_t n_rows, egnn_stream_t stream);
 
 /* ---- SELL plan: one-time re-layout of a binary, column-sorted CSR -----------
  * New in this build (no reference counterpart: scipy streams plain CSR).  For
@@ -125,24 +129,31 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base,
  *   egnn_sell_prepare    counts (all passes but the last) in `workspace`,
  *                        SYNCHRONISES the stream and fills the size fields;
  *   (caller allocates slice_off[n_slices+1], blk_slice_ptr[n_blocks+1],
- *    idx[n_entries] (uint16, 256-byte aligned), rv_ptr[n+1], vslot[n_vrows], cta_ptr[2*(n_cta+1)],
- *    vpart[n_rowv] float32 scratch: row i's partial sums are
+ *    idx[n_entries] (uint16, 256-byte aligned), rv_ptr[n+1], vslot[n_vrows], cta_info[2*n_cta+64],
+ *    sched[2112] uint32, vpart[n_rowv] float32 scratch: row i's partial sums are
  *    vpart[rv_ptr[i] .. rv_ptr[i+1]), virtual row v writes vpart[vslot[v]])
  *   egnn_sell_fill       writes the index stream; `workspace` must be the
  *                        one prepare used, untouched in between.
- * A plan is read-only afterwards except vpart (one wavelet call at a time). */
+ * A plan is read-only afterwards except vpart and sched (one wavelet call at a
+ * time per plan).                                                             */
 typedef struct egnn_sell_plan {
     int32_t n, n_blocks, col_block, lmax; /* n: rows laid out (a row shard or the whole graph) */
     int32_t n_cols, row0;                 /* columns = global nodes; global id of row 0        */
-    int32_t n_cta, reserved;              /* CTAs of the order kernel (set by prepare: SM count) */
+    int32_t n_cta, reserved;              /* CTAs of the step kernel (set by prepare: SM count, one per SM) */
     int64_t n_slices, n_vrows, n_entries, n_rowv;
     int32_t* slice_off;
     int32_t* blk_slice_ptr;
     uint16_t* idx;
     int32_t* rv_ptr;
     int32_t* vslot;
-    int32_t* cta_ptr;                     /* [2 * (n_cta + 1)] slice range, then first column block, of every CTA (egnn_sell_fill) */
+    int32_t* cta_info;                    /* [2 * n_cta + 64]: column block and rank inside it of every CTA, start value
+                                             of every block's slice counter (egnn_sell_fill)                          */
     float* vpart;
+    uint32_t* sched;                      /* [2112] slice counters (one 128-byte line per column block) + grid-barrier
+                                             counter of the step kernel (egnn_sell_fill
+                                             initialises them; the kernel leaves them ready for the next launch)      */
+    uint64_t* stamps;                     /* optional [4 + 2 * orders per launch]: globaltimer of CTA 0 at kernel start,
+                                             after every grid barrier and at the end (phase breakdown for bench.py)   */
 } egnn_sell_plan;
 
 int egnn_sell_geometry(int64_t n_cols, int64_t nnz, int32_t* n_blocks, int32_t* col_block, int32_t* lmax);
@@ -238,7 +249,9 @@ int egnn_calibration_metrics(const float* x, int32_t is_log, const int64_t* labe
  *   1 = remote columns + acc_ws, then the fused epilogue,
  *   2 = the unsplit rows in one launch (rowptr_local/colidx_local = full CSR
  *       of the rank's rows).
- * nnz_hint sizes the lane layout (mean row length of the launched half).    */
+ * nnz_hint sizes the lane layout (mean row length of the launched half).
+ * delta_*: edge flips with GLOBAL ids (UGCA recompute on a sharded graph),
+ * applied by the launch that sees the exchanged operand (phase 1 or 2).      */
 int egnn_cheb_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_local,
                             const int32_t* rowptr_remote, const int32_t* colidx_remote,
                             const float* dinv_full, const uint8_t* iso_full,
@@ -249,6 +262,8 @@ int egnn_cheb_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
                             int32_t f, int32_t order, int32_t k_max, int32_t n_scales,
                             const float* coeffs_host, float op_scale, float op_shift,
                             int32_t normalize_l1, int32_t phase,
+                            const int32_t* delta_row_host, const int32_t* delta_col_host,
+                            const float* delta_val_host, int32_t n_delta,
                             egnn_stream_t stream);
 
 /* ---- exchange window over peer memory (NVLink / NVSwitch) -------------------
@@ -283,26 +298,41 @@ int egnn_peer_error(const egnn_peer_window* win, int32_t* error_out, egnn_stream
 int egnn_peer_wait_stats(const egnn_peer_window* win, uint64_t* total_ns, uint64_t* waits,
                          int32_t reset, egnn_stream_t stream);
 
-/* One order of the narrow (F = 1) path on a row shard: SELL SpMV over the
- * rank's plan (plan->n rows starting at plan->row0, plan->n_cols columns)
- * against the exchanged full operand y_prev_full = dinv (.) T_{k-1} [n_cols],
- * then the epilogue on the local rows: T_k -> t_out_local (or NULL),
- * dinv (.) T_k -> y_out_local (the slab the next exchange moves; or NULL),
- * scale accumulation into out_local [rows, n_scales].
- * With win_or_null given the exchange is fused: the SpMV waits for the peers'
- * flags and reads operand buffer (order-1)&1 of the window - unless
- * y_prev_full is also given, in which case that vector is the operand and
- * nothing is waited for (an operand every rank already holds, e.g. the
- * default signal at order 1) - and the epilogue stores dinv (.) T_k into
- * buffer order&1 of EVERY rank's window and signals (y_out_local is ignored). */
-int egnn_sell_order_sharded(const egnn_sell_plan* plan, const float* y_prev_full,
-                            const float* dinv_full, const uint8_t* iso_full,
-                            const float* t_prev_local, const float* t_prev2_local,
-                            float* t_out_local, float* y_out_local, float* out_local,
-                            int32_t order, int32_t k_max, int32_t n_scales,
-                            const float* coeffs_host, float op_scale, float op_shift,
-                            int32_t normalize_l1, egnn_stream_t stream,
-                            const egnn_peer_window* win_or_null);
+/* The narrow (F = 1) path on a row shard: orders order_begin..order_end of
+ * the step in ONE persistent cooperative launch over the rank's plan (plan->n
+ * rows starting at plan->row0, plan->n_cols columns; csrc/sell_step.cuh).
+ * Per order: SELL SpMV against the full operand dinv (.) T_{k-1} [n_cols],
+ * grid barrier, epilogue on the local rows (T_k, scale accumulation into
+ * out_local [rows, n_scales], next operand dinv (.) T_k), grid barrier.
+ *   x0_local        [rows] T_0 of the own rows
+ *   tbuf0/tbuf1     [rows] each: T_k (k >= 1) lives in tbuf[(k-1)&1]; the same
+ *                   two buffers must be passed to every call of a step
+ *   t_all_or_null   [k_max+1, rows]: every order stored (then tbuf* unused);
+ *                   the caller fills row block 0 with T_0
+ *   delta_*         edge flips (GLOBAL row/col ids, host arrays) applied on
+ *                   top of the plan; dinv/iso/x0 must describe the perturbed graph
+ * With win_or_null (world > 1) the exchange is fused and the whole step is one
+ * call (order_begin = 1, order_end = k_max): before staging a column block the
+ * kernel waits for the flags of the ranks that own those columns, the epilogue
+ * stores dinv (.) T_k into buffer k&1 of EVERY rank's window, and after the
+ * closing grid barrier one CTA raises this rank's flag everywhere.
+ * y_first_full, when given, is the operand of order_begin held by every rank
+ * (e.g. the default signal): it is read from there and nothing is waited for;
+ * when NULL and order_begin == 1 the kernel computes dinv (.) T_0 itself.
+ * Without a window a shard runs ONE order per call on the gathered operand
+ * y_first_full and leaves dinv (.) T_k of its rows in y_slab{k&1} [rows] for the
+ * caller's exchange; a plan that covers all columns' rows (one rank) runs the
+ * whole step with y_slab0/1 [n_cols] as its operand buffers.                 */
+int egnn_sell_step_sharded(const egnn_sell_plan* plan, const float* dinv_full,
+                           const uint8_t* iso_full, const float* x0_local,
+                           const float* y_first_full, float* y_slab0, float* y_slab1,
+                           float* tbuf0, float* tbuf1, float* t_all_or_null, float* out_local,
+                           int32_t order_begin, int32_t order_end, int32_t k_max,
+                           int32_t n_scales, const float* coeffs_host, float op_scale,
+                           float op_shift, int32_t normalize_l1,
+                           const int32_t* delta_row_host, const int32_t* delta_col_host,
+                           const float* delta_val_host, int32_t n_delta,
+                           const egnn_peer_window* win_or_null, egnn_stream_t stream);
 
 /* y[r, :] = dinv_full[row0 + r] * x[r, :]: the gather operand of order 1 on
  * the narrow path (later orders get it from the epilogue).                   */
@@ -325,7 +355,8 @@ int egnn_peer_prescale_push(const float* x_local, const float* dinv_full, int64_
  * dinv (.) T_k of the own rows into buffer order&1 of EVERY rank's window, then
  * signals.  win->f must be f rounded up to a multiple of 4.  x0_local: exact
  * T_0 rows (order 1 only).  t_out_local_or_null: T_k rows [rows, f] when the
- * caller wants every order.  row_order_or_null: egnn_row_order of the shard.  */
+ * caller wants every order.  row_order_or_null: egnn_row_order of the shard.
+ * delta_*: edge flips with GLOBAL ids applied on top of the shard's CSR.      */
 int egnn_wide_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_local,
                             const float* vals_or_null, const int32_t* row_order_or_null,
                             const float* dinv_full, const uint8_t* iso_full,
@@ -333,21 +364,24 @@ int egnn_wide_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
                             int64_t n_global, int64_t row_begin, int64_t row_end,
                             int32_t f, int32_t order, int32_t k_max, int32_t n_scales,
                             const float* coeffs_host, float op_scale, float op_shift,
-                            int32_t normalize_l1, const egnn_peer_window* win,
-                            egnn_stream_t stream);
+                            int32_t normalize_l1,
+                            const int32_t* delta_row_host, const int32_t* delta_col_host,
+                            const float* delta_val_host, int32_t n_delta,
+                            const egnn_peer_window* win, egnn_stream_t stream);
 
 /* Degree pass of a row shard (scipy semantics as egnn_graph_prep).  phase 0:
  * row sums of the local rows, their diagonal entries into diag_full[row_begin..]
  * and the shard's contribution to the in-degree in colsum_full (both zeroed
  * first); the caller then sums colsum_full and diag_full over the ranks
- * (all-reduce).  phase 1: dinv/iso of every node and x0 = log1p(rowsum) of the
- * local rows.                                                                 */
+ * (all-reduce).  phase 1: dinv/iso of every node (and the in-degree weight w
+ * into w_full_or_null, kept for egnn_patch_degrees) and x0 = log1p(rowsum) of
+ * the local rows.                                                             */
 int egnn_graph_prep_sharded(const int32_t* rowptr_local, const int32_t* colidx_local,
                             const float* vals_or_null, int64_t n_global, int64_t row_begin,
                             int64_t n_rows, int32_t phase, double* colsum_full, float* diag_full,
                             float* rowsum_local, float* dinv_full, uint8_t* iso_full,
                             float* x0_local, int32_t* unsorted_flag_or_null,
-                            egnn_stream_t stream);
+                            float* w_full_or_null, egnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,9 +1,15 @@
-"""Import the *unmodified* reference modules for this path inside the build
-container (TEST INFRASTRUCTURE ONLY; ``/root/reference`` does not exist on the
-GPU box, so nothing that runs there may call :func:`load_reference`).
+"""Import the *unmodified* reference modules for this path (TEST
+INFRASTRUCTURE ONLY: ``tests/``, ``smoke()`` and the CPU legs of ``bench.py``).
 
-A plain ``import calibration.WATS`` fails here because the package
-``__init__`` pulls matplotlib (calibration/__init__.py:20 -> TS.py:17) and
+Two places can hold them:
+
+* ``/root/reference`` - the reference checkout, mounted in the build container
+  only;
+* ``oracle/_ref/`` - the same modules byte-compiled by ``oracle/build_ref.py``
+  (sourceless ``.pyc``, git-ignored, travels to the GPU box with the snapshot).
+
+A plain ``import calibration.WATS`` fails because the package ``__init__``
+pulls matplotlib (calibration/__init__.py:20 -> TS.py:17) and
 ``utils/ece.py:3,6`` imports matplotlib/seaborn at top level.  We register
 bare package modules (so the ``__init__`` files never run) and empty stubs for
 the plotting libraries, then import the three files the path needs.
@@ -16,16 +22,38 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("EGNN_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _has(root: str, ext: str) -> bool:
+    return os.path.isfile(os.path.join(root, "calibration", "WATS" + ext))
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "calibration", "WATS.py"))
+    """The reference checkout itself is mounted (build container)."""
+    return _has(REFERENCE_ROOT, ".py")
 
 
-def load_reference():
+def staged_available() -> bool:
+    """``oracle/_ref`` holds the byte-compiled reference modules."""
+    return _has(STAGED_ROOT, ".pyc")
+
+
+def reference_root():
+    """Where :func:`load_reference` will import from, or None."""
+    if reference_available():
+        return REFERENCE_ROOT
+    if staged_available():
+        return STAGED_ROOT
+    return None
+
+
+def load_reference(root=None):
     """Returns ``(wats_module, model_module, ece_module)`` of the reference."""
-    if not reference_available():
-        raise RuntimeError(f"reference not mounted at {REFERENCE_ROOT}")
+    root = root or reference_root()
+    if root is None:
+        raise RuntimeError(f"reference neither mounted at {REFERENCE_ROOT} nor staged in {STAGED_ROOT} "
+                           "(run __graft_entry__.build() where /root/reference exists)")
     for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):
         if name not in sys.modules:
             try:
@@ -36,11 +64,15 @@ def load_reference():
         setattr(sys.modules["matplotlib"], "pyplot", sys.modules["matplotlib.pyplot"])
     for pkg, rel in (("calibration", "calibration"), ("src", "src"),
                      ("src.gnn", os.path.join("src", "gnn")), ("utils", "utils")):
-        if pkg not in sys.modules or not getattr(sys.modules[pkg], "__egnn_shim__", False):
+        have = sys.modules.get(pkg)
+        if have is None or getattr(have, "__egnn_shim__", None) != root:
+            for name in [m for m in sys.modules if m == pkg or m.startswith(pkg + ".")]:
+                del sys.modules[name]                   # stale import from the other root
             mod = types.ModuleType(pkg)
-            mod.__path__ = [os.path.join(REFERENCE_ROOT, rel)]
-            mod.__egnn_shim__ = True
+            mod.__path__ = [os.path.join(root, rel)]
+            mod.__egnn_shim__ = root
             sys.modules[pkg] = mod
+    importlib.invalidate_caches()
     wats = importlib.import_module("calibration.WATS")
     model = importlib.import_module("src.gnn.model")
     ece = importlib.import_module("utils.ece")

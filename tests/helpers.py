@@ -36,7 +36,7 @@ def rel_max_err(got, ref):
 ELEMENT_FLOOR = 5e-2
 
 
-def elementwise_ratio(got, ref, tol=1e-5):
+def elementwise_ratio(got, ref, tol=1e-5, floor=None):
     """max over elements of |delta| / (tol * max(|ref|, ELEMENT_FLOOR * ||ref||_inf)); <= 1 passes.
 
     SURVEY 8c proposed a floor of 1e-3 * ||ref||_inf, i.e. an absolute error of
@@ -44,10 +44,12 @@ def elementwise_ratio(got, ref, tol=1e-5):
     sum cancels, so no float32 implementation can meet it.  With the floor at
     5e-2 the bound is ~8 eps * ||ref||_inf absolute, which leaves room for the
     O(k^2 eps) growth of the three-term recurrence.  The norm-wise 1e-5 bound
-    (north_star) is checked separately and is met with ~100x margin."""
+    (north_star) is checked separately and is met with ~100x margin.
+    ``floor`` overrides the floor (tests print the ratio at SURVEY's 1e-3 next to
+    the enforced one so the gap stays visible; DESIGN.md section 2 records both)."""
     ref = np.asarray(ref, dtype=np.float64)
     got = np.asarray(got, dtype=np.float64)
-    floor = ELEMENT_FLOOR * np.abs(ref).max()
+    floor = (ELEMENT_FLOOR if floor is None else floor) * np.abs(ref).max()
     return float((np.abs(got - ref) / (tol * np.maximum(np.abs(ref), floor) + 1e-300)).max())
 
 

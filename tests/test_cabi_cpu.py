@@ -68,3 +68,14 @@ def test_heat_coefficients_match_reference_defaults():
     c = egnn.heat_coefficients(3, 0.8)
     np.testing.assert_allclose(c[0], [1.0, 0.449329, 0.201897, 0.090718], atol=1e-6)
     assert egnn.heat_coefficients(2, [0.4, 0.8]).shape == (2, 3)
+
+
+def test_shared_library_is_not_older_than_its_sources():
+    """A stale build (sources edited, library not rebuilt) corrupts arguments silently when a
+    signature changed; catch it here, on the CPU box, before the snapshot travels."""
+    import glob
+    from efficient_gnn_b200 import _cabi
+    src = glob.glob(os.path.join(os.path.dirname(_cabi.LIB_PATH), "..", "csrc", "*.cu*")) + \
+        [os.path.join(ROOT, "include", "egnn_b200.h")]
+    newest = max(os.path.getmtime(f) for f in src)
+    assert os.path.getmtime(_cabi.LIB_PATH) >= newest, "rebuild: efficient-gnn_b200/csrc/build.sh"

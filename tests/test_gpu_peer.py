@@ -24,7 +24,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, k, scales, steps, out_dir, f=1):
+def _flips(n):
+    """Symmetric flips around one target node, spread over both shards (calib_fga.py:897-904)."""
+    target, others = 11, [3, 17, n // 2 + 5, n - 2, n // 3]
+    return target, others
+
+
+def _worker(rank, world, port, k, scales, steps, out_dir, f=1, flips=False):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -40,30 +46,54 @@ def _worker(rank, world, port, k, scales, steps, out_dir, f=1):
         if f != 1:                                   # f == -1: a custom one-column signal (order-1 operand is exchanged too)
             x0_full = np.random.default_rng(abs(f)).standard_normal((n, abs(f))).astype(np.float32)
             x0 = torch.from_numpy(x0_full[sw.row_begin:sw.row_end]).to(dev)
+        deltas = None
+        if flips:                                    # UGCA recompute on the sharded graph: global ids, same list on every rank
+            dense_row = torch.zeros(n)
+            target, others = _flips(n)
+            dense_row[ci[rp[target]:rp[target + 1]].long()] = 1.0
+            rows, cols, vals = [], [], []
+            for j in others:
+                v = float(-2 * dense_row[j].item() + 1)
+                rows += [target, j]; cols += [j, target]; vals += [v, v]
+            deltas = (rows, cols, vals)
         outs = []
-        for _ in range(steps):                       # consecutive steps reuse the two operand buffers
-            outs.append(sw.features(k=k, s=scales, X0_local=x0).cpu().numpy())
-        feats, orders, comb = sw.features(k=k, s=scales, X0_local=x0, return_parts=True)
-        assert sw.exchange_error() == 0, "a flag wait timed out"
+        for step in range(steps):                    # consecutive steps reuse the two operand buffers
+            outs.append(sw.features(k=k, s=scales, X0_local=x0, deltas=deltas).cpu().numpy())
+            if flips and step == 0:                  # perturbed and unperturbed steps interleave in the UGCA loop
+                sw.features(k=k, s=scales, X0_local=x0)
+        feats, orders, comb = sw.features(k=k, s=scales, X0_local=x0, return_parts=True, deltas=deltas)
+        sw.check_exchange()                          # raises if a flag wait timed out
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), b=sw.row_begin, e=sw.row_end,
                  fused=np.stack(outs), comb=comb.cpu().numpy(), **{f"t{i}": o.cpu().numpy() for i, o in enumerate(orders)})
-        sw.peer.close()
-        for px in sw._wide_peers.values():
-            px.close()
+        sw.close()
+        assert sw.peer is None and not sw._wide_peers
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,scales,f", [(3, 0.8, 1), (4, [0.8, 1.6], 1), (1, 0.8, 1), (3, [0.8, 1.6], -1),
-                                        (3, [0.8, 1.6], 16), (4, 0.8, 130)])
-def test_two_rank_fused_exchange_matches_oracle(tmp_path, k, scales, f):
+# steps > 3 with even K: the buffer the first producer of a step fills was read by the peers'
+# last order of the previous step (the wait-before-first-store of the step kernel)
+@pytest.mark.parametrize("k,scales,f,steps,flips", [
+    (3, 0.8, 1, 3, False), (4, [0.8, 1.6], 1, 12, False), (6, 0.8, 1, 8, False), (2, 0.8, 1, 8, False),
+    (1, 0.8, 1, 3, False), (3, [0.8, 1.6], -1, 3, False), (4, 0.8, -1, 8, False),
+    (3, [0.8, 1.6], 16, 3, False), (4, 0.8, 130, 3, False),
+    (3, 0.8, 1, 3, True), (4, [0.8, 1.6], 1, 4, True), (3, 0.8, 16, 3, True)])
+def test_two_rank_fused_exchange_matches_oracle(tmp_path, k, scales, f, steps, flips):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (one process per GPU)")
     import torch.multiprocessing as mp
-    world, steps = 2, 3
-    mp.spawn(_worker, args=(world, _free_port(), k, scales, steps, str(tmp_path), f), nprocs=world, join=True)
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), k, scales, steps, str(tmp_path), f, flips), nprocs=world, join=True)
     rp, ci, n = synth.synth_csr(SHAPE, self_loops=True)
     adj = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
+    if flips:
+        dense = adj.toarray()
+        target, others = _flips(n)
+        for j in others:
+            v = -2 * dense[target, j] + 1
+            dense[target, j] += v
+            dense[j, target] += v
+        adj = sp.csr_matrix(dense.astype(np.float32))
     x0_full = None if f == 1 else np.random.default_rng(abs(f)).standard_normal((n, abs(f))).astype(np.float32)
     p = orc.wavelet_parts(adj, k=k, s=scales, x0=x0_full)
     want_h = np.concatenate(p["H"], axis=1).astype(np.float32)

@@ -51,7 +51,7 @@ class ThreadComm:
         sh["barrier"].wait()
 
 
-def run_world(world, rp, ci, n, f, k, scales, use_sell, x0_full):
+def run_world(world, rp, ci, n, f, k, scales, use_sell, x0_full, deltas=None):
     shared = {"barrier": threading.Barrier(world), "parts": [None] * world, "slabs": [None] * world}
     results, errors = [None] * world, []
 
@@ -65,8 +65,8 @@ def run_world(world, rp, ci, n, f, k, scales, use_sell, x0_full):
             if use_sell:
                 assert sw.plan is not None and sw.plan.row0 == part.begin(rank)
             x0 = None if x0_full is None else torch.from_numpy(x0_full[sw.row_begin:sw.row_end]).cuda()
-            feats, orders, comb = sw.features(k=k, s=scales, X0_local=x0, return_parts=True)
-            fused = sw.features(k=k, s=scales, X0_local=x0)
+            feats, orders, comb = sw.features(k=k, s=scales, X0_local=x0, return_parts=True, deltas=deltas)
+            fused = sw.features(k=k, s=scales, X0_local=x0, deltas=deltas)
             results[rank] = (sw.row_begin, sw.row_end, [o.cpu().numpy() for o in orders], feats.cpu().numpy(),
                              fused.cpu().numpy(), sw.gather_features(fused).cpu().numpy())
         except Exception as exc:          # surface in the main thread, do not deadlock the barrier
@@ -113,3 +113,30 @@ def test_single_rank_sharded_equals_single_gpu_path():
     for x, y in zip(a.orders, orders):
         assert rel_max_err(y.cpu().numpy(), x.cpu().numpy()) <= 2e-6
     assert torch.equal(sw.dinv, g.dinv) and torch.equal(sw.iso, g.iso) and torch.equal(sw.x0, g.x0)
+
+
+@pytest.mark.parametrize("world,f,use_sell", [(2, 1, True), (3, 1, True), (2, 1, False), (2, 8, False)])
+def test_sharded_edge_flips_match_oracle(world, f, use_sell):
+    """UGCA recompute on a row-sharded graph (BASELINE config 5): flips with global ids on top of
+    the shards' CSR / SELL plans, against the oracle on the rebuilt adjacency."""
+    shape = synth.GraphShape("t", 6001, 260_000, 3, 33, 1)
+    rp, ci, n = synth.synth_csr(shape, self_loops=True)
+    dense = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n)).toarray()
+    target, others = 11, [3, 17, n // 2 + 5, n - 2, n // 3]
+    rows, cols, vals = [], [], []
+    for j in others:
+        v = float(-2 * dense[target, j] + 1)
+        dense[target, j] += v
+        dense[j, target] += v
+        rows += [target, j]; cols += [j, target]; vals += [v, v]
+    x0_full = None if f == 1 else np.random.default_rng(f).standard_normal((n, f)).astype(np.float32)
+    k, scales = 3, [0.8, 1.6]
+    p = orc.wavelet_parts(sp.csr_matrix(dense), k=k, s=scales, x0=x0_full)
+    res = run_world(world, rp.cuda(), ci.cuda(), n, f, k, scales, use_sell, x0_full, deltas=(rows, cols, vals))
+    want = np.concatenate(p["H"], axis=1)
+    sure = np.concatenate([np.abs(sj) > 1e-4 * np.abs(sj).max() for sj in p["S"]], axis=1)
+    for b, e, orders, feats, fused, gathered in res:
+        for got, ref in zip(orders, p["T"]):
+            assert np.abs(got - ref[b:e]).max() / np.abs(ref).max() <= 1e-5
+        m = sure[b:e]
+        np.testing.assert_allclose(fused[m], want[b:e][m], atol=2e-5)

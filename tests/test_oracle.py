@@ -98,9 +98,17 @@ def test_ece_matches_reference_formula():
     assert abs(orc.classwise_ece(probs, y, 2) - total) < 1e-15
 
 
-@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference not mounted")
-def test_against_live_reference():
-    wats, _model, ece = ref_shim.load_reference()
+@pytest.mark.skipif(ref_shim.reference_root() is None, reason="reference neither mounted nor staged in oracle/_ref")
+@pytest.mark.parametrize("where", ["mounted", "staged"])
+def test_against_live_reference(where):
+    """The restatement against the reference's own code: the checkout in the build
+    container, and the byte-compiled copy in oracle/_ref that travels to the GPU box."""
+    root = ref_shim.REFERENCE_ROOT if where == "mounted" else ref_shim.STAGED_ROOT
+    if (where == "mounted" and not ref_shim.reference_available()) or \
+            (where == "staged" and not ref_shim.staged_available()):
+        pytest.skip(f"reference not {where}")
+    wats, _model, ece = ref_shim.load_reference(root)
+    assert wats.__file__.startswith(root)
     from efficient_gnn_b200 import synth
     rp, ci, n = synth.synth_csr(synth.GraphShape("t", 1500, 9000, 3, 77, 1), self_loops=True)
     adj = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))

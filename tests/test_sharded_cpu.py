@@ -36,11 +36,27 @@ class NumpyEngine:
         w = colsum.numpy().astype(np.float32) - diag.numpy()
         iso = w == 0
         dinv = np.where(iso, 1.0, 1.0 / np.sqrt(np.where(iso, 1.0, w).astype(np.float64))).astype(np.float32)
+        self.w_full, self.rowsum_local = w.copy(), rowsum.copy()
         return (torch.from_numpy(dinv), torch.from_numpy(iso.astype(np.uint8)),
                 torch.from_numpy(np.log1p(rowsum)), False)
 
+    def patch_degrees(self, dinv, iso, x0_local, n_global, row_begin, n_rows, deltas):
+        """Host restatement of egnn_patch_degrees on a row shard."""
+        w, rowsum = self.w_full.copy(), self.rowsum_local.copy()
+        for r, c, v in zip(*deltas):
+            if r != c:
+                w[c] += v
+            if row_begin <= r < row_begin + n_rows:
+                rowsum[r - row_begin] += v
+        is_iso = w == 0
+        d2 = np.where(is_iso, 1.0, 1.0 / np.sqrt(np.where(is_iso, 1.0, w).astype(np.float64))).astype(np.float32)
+        return (torch.from_numpy(d2), torch.from_numpy(is_iso.astype(np.uint8)),
+                torch.from_numpy(np.log1p(rowsum).astype(np.float32)))
+
     def sell_plan(self, *a, **k):
-        return None
+        return self.fake_plan
+
+    fake_plan = None
 
     def fork(self):
         self.calls.append("fork")
@@ -54,7 +70,7 @@ class NumpyEngine:
 
     def order(self, phase, local, remote, dinv, iso, t_prev_full, t_prev_local, t_prev2_local, t_out_local,
               out_local, acc_ws, n_global, nnz_hint, row_begin, row_end, f, order, k_max, n_scales, coeffs,
-              op_scale, op_shift, normalize):
+              op_scale, op_shift, normalize, deltas=None):
         self.calls.append(f"order{order}.phase{phase}")
         rows = row_end - row_begin
         rp, ci = (local if phase == 0 else remote)
@@ -66,6 +82,11 @@ class NumpyEngine:
         r = np.repeat(np.arange(rows), np.diff(rp))
         keep = ci != (r + row_begin)
         np.add.at(acc, r[keep], d[ci[keep], None] * src[ci[keep] - off])
+        if deltas is not None:
+            assert phase != 0                  # flips ride with the launch that sees the exchanged operand
+            for dr, dc, dv in zip(*deltas):
+                if row_begin <= dr < row_end and dr != dc:
+                    acc[dr - row_begin] += dv * d[dc] * src[dc]
         if phase == 0:
             acc_ws.numpy()[:rows] = acc
             return
@@ -156,3 +177,80 @@ def test_row_partition_and_split():
     (lp, lc), (rp, rc) = sharded.split_columns(rowptr, colidx, 0, 3)
     assert lp.tolist() == [0, 1, 3, 3] and lc.tolist() == [0, 1, 2]
     assert rp.tolist() == [0, 1, 2, 2] and rc.tolist() == [7, 9]
+
+
+def _delta_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from efficient_gnn_b200 import sharded, synth
+        from oracle import wats_oracle as orc
+        rp, ci, n = synth.synth_csr(synth.GraphShape("t", 901, 8000, 3, 33, 1), self_loops=True)
+        adj = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
+        dense = adj.toarray()
+        # calib_fga.py:897-904: symmetric flips incident to one target node, across shard boundaries
+        target, others = 5, [7, 300, 450, 700, 899]
+        rows, cols, vals = [], [], []
+        pert = dense.copy()
+        for j in others:
+            v = float(-2 * dense[target, j] + 1)
+            pert[target, j] += v
+            pert[j, target] += v
+            rows += [target, j]; cols += [j, target]; vals += [v, v]
+        part = sharded.RowPartition(n, world)
+        rpl, cil = part.slice_csr(rp, ci, rank)
+        sw = sharded.ShardedWavelet(rpl, cil, n, engine=NumpyEngine(), device="cpu")
+        feats, orders, comb = sw.features(k=3, s=[0.8, 1.6], return_parts=True, deltas=(rows, cols, vals))
+        p = orc.wavelet_parts(sp.csr_matrix(pert.astype(np.float32)), k=3, s=[0.8, 1.6])
+        b, e = sw.row_begin, sw.row_end
+        for got, ref in zip(orders, p["T"]):
+            np.testing.assert_allclose(got.numpy(), ref[b:e], atol=2e-5)
+        np.testing.assert_allclose(feats.numpy(), np.concatenate(p["H"], axis=1)[b:e], atol=2e-5)
+        # and the unperturbed graph is untouched by the call
+        base = sw.features(k=3, s=0.8)
+        np.testing.assert_allclose(base.numpy(), orc.wavelet_features(adj, k=3, s=0.8)[b:e], atol=2e-5)
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_edge_flips_gloo():
+    """UGCA recompute on a row-sharded graph (BASELINE config 5): global flip list, every rank
+    patches its replicated degree vectors and applies the flips of the rows it owns."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_delta_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert [ret.get(r) for r in range(2)] == ["ok"] * 2
+
+
+def _mixed_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from efficient_gnn_b200 import sharded, synth
+        rp, ci, n = synth.synth_csr(synth.GraphShape("t", 400, 3000, 3, 11, 1), self_loops=True)
+        part = sharded.RowPartition(n, world)
+        rpl, cil = part.slice_csr(rp, ci, rank)
+        eng = NumpyEngine()
+        eng.fake_plan = object() if rank == 0 else None      # only rank 0's shard qualifies for the SELL plan
+        sw = sharded.ShardedWavelet(rpl, cil, n, engine=eng, device="cpu")
+        ret[rank] = "no plan" if sw.plan is None else "plan"
+        feats = sw.features(k=2, s=0.8)                       # and the generic path still runs on both
+        assert feats.shape == (sw.rows, 1)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ranks_agree_on_the_narrow_path_gloo():
+    """A rank whose shard does not qualify for the SELL plan takes it away from every rank:
+    the plan path exchanges dinv*T, the generic path plain T - a mixed world would silently
+    read each other's slabs as the wrong quantity."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_mixed_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert [ret.get(r) for r in range(2)] == ["no plan", "no plan"]
