@@ -6,17 +6,36 @@
                     [--workload reddit|arxiv|physics|pubmed|cora] [--f F] [--order K] [--scales S]
 
 One "step" = one pass of the hot path over one synthetic graph of the named
-shape: K fused Chebyshev orders (CSR SpMM over the implicit scaled Laplacian +
+shape: K fused Chebyshev orders (SpMM over the implicit scaled Laplacian +
 recurrence + scale accumulation + L1 normalisation).  Default workload: the
-Reddit shape (232,965 nodes, 114.6 M stored entries) with the reference's
+Reddit shape (232,965 nodes, 114.8 M stored entries) with the reference's
 defaults K=3, S=1 (s=0.8), F=1 (X0 = log1p(degree)) - the largest named
-configuration; it fits one B200 and is the only one whose CSR streams from HBM.
+configuration; it fits one B200 and is the only one whose index stream comes
+from HBM every order.
 
-Prints ONE JSON line (see README/DESIGN.md for the keys).  `value` is timed with
-the graph resident in HBM; `e2e` is the same metric through the host-buffer
-entry (pinned host CSR -> H2D -> degree pass -> orders -> D2H of the features).
-`--impl reference` times the CPU oracle port of the reference's scipy path
-(the reference itself is pure Python + scipy and is not present on the GPU box).
+Prints ONE JSON line (DESIGN.md section 7 explains the keys):
+
+* ``value``: graph resident in HBM, whole step timed on the device;
+* ``roofline``: the dominant kernel (the persistent step kernel of the narrow
+  path = K orders in one launch) against the measured HBM copy bandwidth -
+  ``achieved``/``frac`` on the bytes the kernel itself must stream (2-byte
+  block-local indices + slice tables + per-order vectors), ``achieved_contract``
+  on SURVEY 8d's int32-CSR model, ``b_gather`` on the north star's gathered-rows
+  model, the phase split from the kernel's own timestamps, ``traffic`` from the
+  ncu capture recorded in profiles/dram_traffic.json;
+* ``roofline_wide``: the two wide shapes the >= 70 % target names (arxiv-shape
+  F=128, Reddit-shape F=64), measured in the same run;
+* ``ugca``: the per-perturbation recompute (5 symmetric flips around a target
+  node on top of the resident graph), device-timed and end to end
+  (host flip list in -> features on the host);
+* ``e2e``: the same metric through the host-buffer entry (pinned host CSR ->
+  H2D -> degree pass -> orders -> D2H of the features);
+* ``cpu_baseline`` / ``--impl reference``: the REFERENCE's own
+  ``graph_wavelet_features`` (calibration/WATS.py:39-74), byte-compiled into
+  oracle/_ref by ``__graft_entry__.build()``, on the SAME full graph, scipy on
+  one host core as the reference runs it, with the Laplacian / rescale /
+  recurrence split of WATS.py:53,55,62.  Falls back to the oracle port
+  (``kind: "port"``) when oracle/_ref is not staged.
 """
 from __future__ import annotations
 
@@ -37,7 +56,8 @@ import torch  # noqa: E402
 METRIC = "chebyshev_wavelet_nnz_k_f_per_s"
 UNIT = "nnz*K*F/s"
 DEFAULT_F = {"reddit": 1, "arxiv": 128, "physics": 1, "pubmed": 1, "cora": 1}
-CPU_RATE_GUESS = 2.0e7      # nnz*K*F/s of the oracle port on one host core (sizes the bounded CPU sample)
+REFERENCE_MAX_TIMED_RUNS = 2     # stock-function runs of the reference arm (the full Reddit graph takes ~1 min each)
+REFERENCE_FULL_GRAPH_LIMIT = 8   # K*F above which the CPU arm falls back to a scaled sample of the workload
 
 
 def parse_args():
@@ -52,6 +72,8 @@ def parse_args():
     ap.add_argument("--scales", type=int, default=1, help="number of wavelet scales S")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-wide", action="store_true", help="skip the roofline_wide sub-records")
+    ap.add_argument("--no-ugca", action="store_true", help="skip the ugca sub-record")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
     ap.add_argument("--entry", default="csr", choices=["csr", "dense"],
                     help="e2e entry: pinned host CSR (default) or the reference's own boundary, a dense [N,N] float32 "
@@ -63,7 +85,8 @@ def parse_args():
     ap.add_argument("--flips", type=int, default=0,
                     help="UGCA mode (N=1): every step recomputes the features of the graph with this many symmetric "
                          "edge flips around a random target node applied on top of the resident graph")
-    ap.add_argument("--check", action="store_true", help="N>1: compare every rank's rows with the single-GPU path")
+    ap.add_argument("--no-check", action="store_true",
+                    help="N>1: skip the comparison of every rank's rows with the single-GPU path (outside the timed region)")
     return ap.parse_args()
 
 
@@ -72,7 +95,18 @@ def scale_list(n_scales):
     return base[0] if n_scales == 1 else base[:n_scales]
 
 
-def algorithmic_bytes(n, nnz, f, k_max, n_scales):
+def workload_config(workload, n, nnz, k, n_scales, f, flips=0):
+    """The ``config`` object: what is computed, identical for both arms."""
+    return {"workload": f"{workload}-shape", "n": int(n), "nnz": int(nnz), "k": int(k), "scales": int(n_scales),
+            "f": int(f), "self_loops": True, "ugca_flips": int(flips),
+            "l2_policy": ("inputs larger than L2 (index stream %.0f MB per order vs 126 MB L2), no flush" % (2 * nnz / 1e6)
+                          if 2 * nnz > 126e6 else "inputs fit in L2: latency-bound configuration, no flush")}
+
+
+# --------------------------------------------------------------------------- #
+# bytes models                                                                  #
+# --------------------------------------------------------------------------- #
+def contract_bytes(n, nnz, f, k_max, n_scales):
     """Compulsory-traffic model B_k of SURVEY 8d (int32 indices, fp32 data,
     binary adjacency) for each order k = 1..K."""
     out = []
@@ -80,6 +114,28 @@ def algorithmic_bytes(n, nnz, f, k_max, n_scales):
         t_terms = 1 + (1 if k >= 2 else 0) + (1 if k < k_max else 0)
         acc = 1 if k == 1 else 2
         out.append(4 * nnz + 4 * (n + 1) + 4 * n + 4 * n * f * t_terms + 4 * n_scales * n * f * acc)
+    return out
+
+
+def gather_bytes(n, nnz, f, k_max, n_scales):
+    """SURVEY 8d's secondary, north-star-literal model B_gather: the T_{k-1} term
+    is one gathered row per stored entry (4*nnz*F) instead of one read of T_{k-1}."""
+    return [b - 4 * n * f + 4 * nnz * f for b in contract_bytes(n, nnz, f, k_max, n_scales)]
+
+
+def sell_stream_bytes(plan, n, k_max, n_scales):
+    """What the narrow-path step kernel itself must move per order:
+    the 2-byte index stream of the padded entries, the slice tables (offset and
+    partial-sum slot per virtual row), the partial sums (written, then read by the
+    epilogue), the row pointers of the partial sums, and the per-row vectors
+    (dinv, iso, T_{k-1}, T_{k-2}, T_k, operand written + staged once, S outputs)."""
+    out = []
+    for k in range(1, k_max + 1):
+        stream = 2 * plan.n_entries + 4 * (plan.n_slices + 1) + 4 * plan.n_vrows
+        partial = 2 * 4 * plan.n_rowv + 4 * (n + 1)
+        t_terms = 1 + (1 if k >= 2 else 0) + (1 if k < k_max else 0)
+        vectors = 4 * n + n + 4 * n * t_terms + (8 * n if k < k_max else 4 * n) + 4 * n_scales * n * (1 if k == 1 else 2)
+        out.append(stream + partial + vectors)
     return out
 
 
@@ -149,65 +205,147 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dram_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the
+    committed `ncu --set full` capture of this configuration (profiles/dram_traffic.json; the
+    capture's summary and command are named there) - None when this configuration has none."""
+    path = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if not os.path.isfile(path):
+        return None, None
+    try:
+        rec = json.load(open(path)).get(key)
+    except Exception:
+        return None, None
+    if rec is None:
+        return None, None
+    if isinstance(rec, dict):
+        return rec.get("bytes_per_launch"), rec.get("source")
+    return rec, "profiles/ (round 1 capture)"
+
+
 # --------------------------------------------------------------------------- #
-# CPU arm: the oracle port of the reference's scipy path                        #
+# CPU arm: the reference's own code (oracle/_ref), else the oracle port         #
 # --------------------------------------------------------------------------- #
-def cpu_sample_graph(workload, target_seconds, k_max, f, gen_device):
-    """A bounded sample of the workload: the same generator at a reduced scale
-    (nodes and entries shrunk together, same mean degree)."""
+def host_graph(workload, scale=1.0):
+    """The workload's synthetic graph as scipy CSR float32, generated on the host."""
     import scipy.sparse as sp
     from efficient_gnn_b200 import synth
-    sh = synth.SHAPES[workload]
-    want_nnz = CPU_RATE_GUESS * target_seconds / max(1, k_max)      # F enters through the recurrence only
-    scale = float(min(1.0, max(2e-3, want_nnz / sh.nnz)))
-    rp, ci, n = synth.synth_csr(workload, self_loops=True, device=gen_device, scale=scale)
-    rp, ci = rp.cpu().numpy(), ci.cpu().numpy()
-    adj = sp.csr_matrix((np.ones(ci.size, np.float32), ci, rp), shape=(n, n))
-    return adj, scale
+    rp, ci, n = synth.synth_csr(workload, self_loops=True, device="cpu", scale=scale)
+    return sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
 
 
-def time_oracle(adj, k_max, scales, f, repeats=1):
-    from oracle import wats_oracle as orc
+def load_reference_wats():
+    """The reference's calibration/WATS.py module (unmodified), or None."""
+    try:
+        from oracle import ref_shim
+        if ref_shim.reference_root() is None:
+            return None
+        return ref_shim.load_reference()[0]
+    except Exception:
+        return None
+
+
+def cpu_path_once(wats, adj, k, scales, f, x0, split):
+    """One pass of the CPU path.  With the reference module and the reference's
+    own configuration (F = 1 default signal, one scale) this is literally
+    ``graph_wavelet_features(adj, k, s)``; other configurations compose the
+    reference's own functions the way that function does.  ``split``: run the
+    three legs of WATS.py:53,55,62 separately and time each."""
+    from scipy.sparse import identity
+    stock = wats is not None and f == 1 and np.ndim(scales) == 0
+    if stock and not split:
+        t0 = time.perf_counter()
+        wats.graph_wavelet_features(adj, k=k, s=scales)
+        return {"total": time.perf_counter() - t0}
+    if wats is None:
+        from oracle import wats_oracle as orc
+        t0 = time.perf_counter()
+        lt = orc.rescaled_laplacian(adj)
+        t1 = time.perf_counter()
+        xx = orc.input_signal(adj) if x0 is None else x0
+        orders = orc.chebyshev_orders(lt, k, xx)
+        t2 = time.perf_counter()
+        for a in orc.heat_coefficients(k, scales):
+            comb = sum(a[i] * orders[i] for i in range(k + 1))
+            comb / (np.abs(comb).sum(axis=1, keepdims=True) + 1e-8)
+        t3 = time.perf_counter()
+        return {"total": t3 - t0, "laplacian_and_rescale": t1 - t0, "recurrence": t2 - t1, "combine": t3 - t2}
+    n = adj.shape[0]
+    t0 = time.perf_counter()
+    lap = wats.compute_normalized_laplacian(adj)                   # WATS.py:53
+    t1 = time.perf_counter()
+    l_rescaled = (2 / 2.0) * lap - identity(n)                     # WATS.py:55
+    t2 = time.perf_counter()
+    xx = np.log1p(np.array(adj.sum(axis=1)).flatten()).reshape(-1, 1) if x0 is None else x0   # WATS.py:58-59
+    t_k = wats.chebyshev_polynomials(l_rescaled, k, xx)            # WATS.py:62
+    t3 = time.perf_counter()
+    for s in np.atleast_1d(scales):                                # WATS.py:65-72 per scale
+        alpha = [np.exp(-s * i) for i in range(k + 1)]
+        comb = sum(alpha[i] * t_k[i] for i in range(k + 1))
+        comb / (np.linalg.norm(comb, ord=1, axis=1, keepdims=True) + 1e-8)
+    t4 = time.perf_counter()
+    return {"total": t4 - t0, "laplacian": t1 - t0, "rescale": t2 - t1, "recurrence": t3 - t2, "combine": t4 - t3}
+
+
+def time_cpu_path(adj, k, scales, f, stock_runs, split_run=True):
+    """Times the CPU arm on ``adj``.  Returns the ``cpu_baseline`` object (value =
+    best stock run, or the split run's total when no stock run was asked for)."""
+    wats = load_reference_wats()
     x0 = None
     if f > 1:
         x0 = np.random.default_rng(3).standard_normal((adj.shape[0], f)).astype(np.float32)
-    best = float("inf")
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        orc.wavelet_features(adj, k=k_max, s=scales, x0=x0)
-        best = min(best, time.perf_counter() - t0)
-    return best
+    runs = [cpu_path_once(wats, adj, k, scales, f, x0, split=False)["total"] for _ in range(stock_runs)]
+    split = cpu_path_once(wats, adj, k, scales, f, x0, split=True) if split_run else None
+    best = min(runs) if runs else split["total"]
+    stock = wats is not None and f == 1 and np.ndim(scales) == 0
+    kind = "reference" if wats is not None else "port"
+    what = ("the reference's own graph_wavelet_features (calibration/WATS.py:39-74, unmodified, byte-compiled in "
+            "oracle/_ref)" if stock else
+            "the reference's own compute_normalized_laplacian / chebyshev_polynomials (calibration/WATS.py:24-37, "
+            "oracle/_ref) composed as graph_wavelet_features does" if wats is not None else
+            "oracle port of calibration/WATS.py:39-74 (oracle/_ref not staged)")
+    return {"value": adj.nnz * k * f / best, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
+            "seconds": best, "runs_seconds": runs, "split_seconds": split,
+            "sample": (f"full graph N={adj.shape[0]}, nnz={adj.nnz}, K={k}, S={np.size(scales)}, F={f}; {what}; scipy is "
+                       f"single-threaded on this path; best of {max(1, len(runs))} run(s)"
+                       + (", plus one run with the Laplacian / rescale / recurrence legs timed separately" if split else ""))}
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the CPU implementation of the path (oracle port of
-    calibration/WATS.py:39-74 over scipy, single-threaded like the reference)
-    on a bounded sample per step."""
+    """`--impl reference`: the reference's CPU implementation of the path on the
+    SAME configuration.  The full Reddit-shape graph costs about a minute per
+    pass on one core, so the arm times min(--steps, 2) passes of the stock
+    function plus one pass with the three legs split, whatever --steps/--warmup
+    say (stated in the line: ``steps`` is what was run)."""
     if rank != 0:
         return
+    from efficient_gnn_b200 import synth
     f = args.f or DEFAULT_F[args.workload]
     scales = scale_list(args.scales)
-    total = max(1, args.steps + args.warmup)
-    per_step = min(10.0, max(0.5, 150.0 / total))
-    adj, scale = cpu_sample_graph(args.workload, per_step, args.order, f, "cpu")
-    for _ in range(args.warmup):
-        time_oracle(adj, args.order, scales, f)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        time_oracle(adj, args.order, scales, f)
-    dt = (time.perf_counter() - t0) / max(1, args.steps)
-    value = adj.nnz * args.order * f / dt
-    sample = (f"{args.workload}-shape generator at scale {scale:.4f} (N={adj.shape[0]}, nnz={adj.nnz}), "
-              f"K={args.order}, S={args.scales}, F={f}; one full path per step")
+    sh = synth.SHAPES[args.workload]
+    scale = 1.0
+    if args.order * f > REFERENCE_FULL_GRAPH_LIMIT and sh.nnz > 5_000_000:
+        scale = max(2e-3, min(1.0, 2.0e8 / (sh.nnz * args.order * f)))       # wide signals: bounded sample of the shape
+    adj = host_graph(args.workload, scale)
+    big = adj.nnz > 20_000_000
+    stock_runs = max(1, min(args.steps, REFERENCE_MAX_TIMED_RUNS if big else 5))
+    base = time_cpu_path(adj, args.order, scales, f, stock_runs, split_run=True)
+    if scale != 1.0:
+        base["sample"] = f"{args.workload}-shape generator at scale {scale:.4f}: " + base["sample"]
+    cfg = workload_config(args.workload, adj.shape[0], adj.nnz, args.order, args.scales, f, args.flips)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}-shape", "k": args.order, "scales": args.scales, "f": f,
-                   "sample_scale": scale, "n": int(adj.shape[0]), "nnz": int(adj.nnz)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores": os.cpu_count()},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": stock_runs, "steps_requested": args.steps, "warmup": 0, "warmup_requested": args.warmup,
+        "ms_per_step": base["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -216,10 +354,73 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------- #
 # GPU arm                                                                       #
 # --------------------------------------------------------------------------- #
+def make_flips(n, budget, seed, graph_rowptr=None, graph_colidx=None):
+    """calib_fga.py:897-904: `budget` symmetric flips incident to one target node (additions here;
+    the kernels treat removals the same way: a -1 delta)."""
+    gen = torch.Generator().manual_seed(seed)
+    picks = torch.randint(0, n, (budget + 1,), generator=gen).tolist()
+    target, others = picks[0], [j for j in picks[1:] if j != picks[0]]
+    return ([target] * len(others) + others, others + [target] * len(others), [1.0] * (2 * len(others)))
+
+
+def time_steps(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def wide_record(egnn, synth, workload, f, graph, dev, peak, k_max=3):
+    """One wide-signal shape through cheb_wide_kernel: per-order CUDA events recorded by the library."""
+    import ctypes as C
+    sh = synth.SHAPES[workload]
+    if graph is None:
+        rp, ci, n = synth.synth_csr(workload, self_loops=True, device=dev)
+        graph = egnn.CsrGraph(rp, ci, None, n)
+    n, nnz = graph.n, graph.nnz
+    x0 = torch.randn(n, f, device=dev, generator=torch.Generator(device=dev).manual_seed(sh.seed))
+    steps = 12
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * k_max)] for _ in range(steps)]
+    for row in ev:
+        for e in row:
+            e.record()
+    torch.cuda.synchronize()
+    arrays = [(C.c_void_p * (2 * k_max))(*[e.cuda_event for e in row]) for row in ev]
+    for _ in range(3):
+        egnn.graph_wavelet_features(graph, k=k_max, s=0.8, X0=x0)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        egnn.graph_wavelet_features(graph, k=k_max, s=0.8, X0=x0, _order_events=arrays[i])
+    b.record()
+    torch.cuda.synchronize()
+    ms_step = a.elapsed_time(b) / steps
+    order_ms = np.array([[row[2 * j].elapsed_time(row[2 * j + 1]) for j in range(k_max)] for row in ev]).mean(axis=0)
+    b_k = contract_bytes(n, nnz, f, k_max, 1)
+    g_k = gather_bytes(n, nnz, f, k_max, 1)
+    avg = float(order_ms.mean())
+    achieved = (sum(b_k) / k_max) / (avg * 1e-3) / 1e9
+    traffic, src = dram_traffic(f"{workload}_f{f}_k{k_max}_s1")
+    return {"workload": f"{workload}-shape", "n": n, "nnz": nnz, "f": f, "k": k_max, "kernel": "cheb_wide_kernel",
+            "ms_per_step": ms_step, "per_order_ms": [float(v) for v in order_ms], "value": nnz * k_max * f / (ms_step * 1e-3),
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "algorithmic_bytes_per_launch": sum(b_k) / k_max,
+            "b_gather_bytes_per_launch": sum(g_k) / k_max, "b_gather_achieved": (sum(g_k) / k_max) / (avg * 1e-3) / 1e9,
+            "traffic": traffic, "traffic_source": src,
+            "note": "contract-bytes model (every T row read once); the gathers are served by L2, see DESIGN.md 4.3"}
+
+
 def run_ours(args, rank, local_rank, world):
-    import torch.distributed as dist
     import efficient_gnn_b200 as egnn
     from efficient_gnn_b200 import synth
+    from efficient_gnn_b200.graph import enable_phase_stamps, read_phase_stamps
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -232,8 +433,8 @@ def run_ours(args, rank, local_rank, world):
         return run_replicas(args, rank, local_rank, world)
     if world > 1:
         from efficient_gnn_b200 import sharded
-        return sharded.bench_entry(args, rank, local_rank, world, METRIC, UNIT, algorithmic_bytes,
-                                   ClockSampler, physical_gpu_index, scale_list)
+        return sharded.bench_entry(args, rank, local_rank, world, METRIC, UNIT, contract_bytes, ClockSampler,
+                                   physical_gpu_index, scale_list, workload_config, make_flips)
 
     # synthetic graph of the named shape, generated directly in HBM
     rp, ci, n = synth.synth_csr(args.workload, self_loops=True, device=dev)
@@ -244,21 +445,25 @@ def run_ours(args, rank, local_rank, world):
     else:
         x0 = torch.randn(n, f, device=dev, generator=torch.Generator(device=dev).manual_seed(sh.seed))
     work = float(nnz) * k_max * f
+    peak, peak_src = hbm_peak()
 
     use_sell = False if args.no_sell else None
-    flips = None
-    if args.flips > 0:               # calib_fga.py:897-904: budget symmetric flips incident to one target node
-        gen = torch.Generator().manual_seed(7)
-        picks = torch.randint(0, n, (args.flips + 1,), generator=gen).tolist()
-        target, others = picks[0], [j for j in picks[1:] if j != picks[0]]
-        flips = ([target] * len(others) + others, others + [target] * len(others), [1.0] * (2 * len(others)))
+    flips = make_flips(n, args.flips, 7) if args.flips > 0 else None
 
     def step(events=None):
         return egnn.graph_wavelet_features(graph, k=k_max, s=scales, X0=x0, deltas=flips, _order_events=events,
                                            _use_sell=use_sell)
 
-    # per-order CUDA events (recorded by the library on the launching stream) on every 8th step of the
-    # timed region: recording them on every step costs ~9 % of the step (6 records + a ctypes array)
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    plan = graph.sell_plan() if (f == 1 and k_max >= 1 and not args.no_sell) else None
+    narrow = plan is not None
+    if narrow:
+        enable_phase_stamps(plan)                  # CTA 0's globaltimer at every grid barrier (no effect on the timing)
+
+    # per-launch CUDA events (recorded by the library on the launching stream) on every 8th step of the
+    # timed region; the other steps replay the same pass as one CUDA graph (public API: WaveletSession)
     EV_STRIDE = 8
     ev_steps = list(range(0, args.steps, EV_STRIDE))
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * k_max)] for _ in ev_steps]
@@ -268,11 +473,6 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.synchronize()
     import ctypes as C
     ev_arrays = [(C.c_void_p * (2 * k_max))(*[e.cuda_event for e in row]) for row in ev]
-
-    for _ in range(max(3, args.warmup)):
-        step()
-    torch.cuda.synchronize()
-    # steps without events replay the same pass as one CUDA graph (public API: WaveletSession)
     session = None
     if flips is None and not args.no_graph and not args.no_sell:
         session = egnn.WaveletSession(graph, k=k_max, s=scales, f=f)
@@ -301,31 +501,86 @@ def run_ours(args, rank, local_rank, world):
     ms_per_step = start.elapsed_time(stop) / args.steps
     value = work / (ms_per_step * 1e-3)
 
-    order_ms = np.array([[row[2 * j].elapsed_time(row[2 * j + 1]) for j in range(k_max)] for row in ev])
-    avg_launch_ms = float(order_ms.mean())
-    b_k = algorithmic_bytes(n, nnz, f, k_max, n_scales)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    b_k = contract_bytes(n, nnz, f, k_max, n_scales)
+    g_k = gather_bytes(n, nnz, f, k_max, n_scales)
+    traffic, traffic_src = dram_traffic(f"{args.workload}_f{f}_k{k_max}_s{n_scales}")
+    if narrow:
+        # one launch = the whole step (K orders): events 0/1 bracket the kernel
+        launch_ms = float(np.mean([row[0].elapsed_time(row[1]) for row in ev]))
+        own = sell_stream_bytes(plan, n, k_max, n_scales)
+        phases = read_phase_stamps(plan, k_max, first_operand_in_kernel=(flips is not None))
+        enable_phase_stamps(plan, False)
+        achieved = sum(own) / (launch_ms * 1e-3) / 1e9
+        spmv_us = float(np.mean(phases["spmv"]))
+        roofline = {
+            "bound": "hbm", "kernel": "sell_step_kernel", "launches_per_step": 1, "orders_per_launch": k_max,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": float(sum(own)), "avg_launch_ms": launch_ms,
+            "bytes_model": "own stream: 2 B x padded entries + slice tables + partial sums + per-row vectors, per order "
+                           "(DESIGN.md 4.2); K orders per launch",
+            "achieved_contract": sum(b_k) / (launch_ms * 1e-3) / 1e9, "frac_contract": sum(b_k) / (launch_ms * 1e-3) / 1e9 / peak,
+            "contract_bytes_per_launch": float(sum(b_k)),
+            "b_gather_bytes_per_launch": float(sum(g_k)), "b_gather_achieved": sum(g_k) / (launch_ms * 1e-3) / 1e9,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "phase_us": phases,
+            "spmv_phase": {"us_per_order": spmv_us, "bytes_per_order": float(own[0]),
+                           "achieved": own[0] / (spmv_us * 1e-6) / 1e9, "frac": own[0] / (spmv_us * 1e-6) / 1e9 / peak,
+                           "note": "operand staging + slices + closing grid barrier of one order, from the kernel's own "
+                                   "globaltimer stamps (last launch of the timed region)"},
+            "kernel_share_of_step": launch_ms / ms_per_step,
+            "padded_entries": int(plan.n_entries), "virtual_rows": int(plan.n_rowv),
+        }
+        launches_per_step = (k_max + 15) // 16 + (1 if flips is not None else 0)
     else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = (sum(b_k) / k_max) / (avg_launch_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.isfile(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(f"{args.workload}_f{f}_k{k_max}_s{n_scales}")
-        except Exception:
-            traffic = None
-    if f == 1 and k_max >= 1 and not args.no_sell and graph.sell_plan() is not None:
-        kernel_name = "sell_spmv_kernel"
-    else:
+        order_ms = np.array([[row[2 * j].elapsed_time(row[2 * j + 1]) for j in range(k_max)] for row in ev])
+        avg_launch_ms = float(order_ms.mean())
+        achieved = (sum(b_k) / k_max) / (avg_launch_ms * 1e-3) / 1e9
         kernel_name = "cheb_wide_kernel" if f >= 8 else "cheb_order_kernel"
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": kernel_name, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": sum(b_k) / k_max, "avg_launch_ms": avg_launch_ms,
-                "per_order_ms": [float(v) for v in order_ms.mean(axis=0)],
-                "order_kernel_share_of_step": float(order_ms.sum(axis=1).mean() / ms_per_step)}
+        roofline = {"bound": "hbm", "kernel": kernel_name, "launches_per_step": k_max, "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": sum(b_k) / k_max, "avg_launch_ms": avg_launch_ms,
+                    "bytes_model": "SURVEY 8d contract bytes B_k (int32 CSR, every T row read once), per order",
+                    "b_gather_bytes_per_launch": sum(g_k) / k_max,
+                    "b_gather_achieved": (sum(g_k) / k_max) / (avg_launch_ms * 1e-3) / 1e9,
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "per_order_ms": [float(v) for v in order_ms.mean(axis=0)],
+                    "kernel_share_of_step": float(order_ms.sum(axis=1).mean() / ms_per_step)}
+        if f >= 8:
+            launches_per_step = 1 + k_max + (1 if (f + 3) // 4 * 4 > 128 else 0)
+        else:
+            launches_per_step = k_max + (1 if f <= 4 else 0)
+
+    # the two wide shapes the >= 70 % target names, in the same run
+    roofline_wide = None
+    if not args.no_wide and args.workload == "reddit" and f == 1 and flips is None:
+        roofline_wide = [wide_record(egnn, synth, "arxiv", 128, None, dev, peak),
+                         wide_record(egnn, synth, "reddit", 64, graph, dev, peak)]
+
+    # UGCA per-perturbation recompute on the resident graph: host flip list in -> features on the host
+    ugca = None
+    if not args.no_ugca and f == 1 and flips is None:
+        budget = 5
+        cands = [make_flips(n, budget, 100 + i) for i in range(64)]
+        it = iter(cands * 8)
+        dev_ms = time_steps(lambda: egnn.graph_wavelet_features(graph, k=k_max, s=scales, deltas=next(it)), 100, 5)
+        out_h = torch.empty((n, n_scales), dtype=torch.float32).pin_memory()
+
+        def ugca_e2e():
+            feats = egnn.graph_wavelet_features(graph, k=k_max, s=scales, deltas=next(it))
+            out_h.copy_(feats, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(5):
+            ugca_e2e()
+        t0 = time.perf_counter()
+        for _ in range(100):
+            ugca_e2e()
+        e_ms = (time.perf_counter() - t0) / 100 * 1e3
+        ugca = {"flips": budget, "recompute_ms": dev_ms, "value": work / (dev_ms * 1e-3),
+                "e2e_ms": e_ms, "e2e_value": work / (e_ms * 1e-3), "h2d_bytes_per_step": 2 * budget * 12,
+                "d2h_bytes_per_step": int(out_h.numel() * 4), "unperturbed_ms": ms_per_step,
+                "entry": "graph_wavelet_features(resident graph, deltas=(rows, cols, vals)): degree patch + step kernel "
+                         "with the flips as kernel arguments (calib_fga.py:868,908,952 recompute point); no CSR/plan rebuild"}
 
     # end to end through the host-buffer entry: pinned CSR -> device -> features -> host
     e2e = None
@@ -370,36 +625,28 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
         e_dt = (time.perf_counter() - t0) / e_steps
         e2e = {"value": work / e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e_dt * 1e3, "steps": e_steps, "entry": entry}
+               "ms_per_step": e_dt * 1e3, "steps": e_steps, "entry": entry,
+               "note": "one-shot use of a fresh graph: generic CSR kernel (the SELL plan pays off from the second use of a "
+                       "graph on); the H2D copy of the CSR is ~80 % of the step"}
 
+    # the reference's own code on the SAME graph (host copy of the resident CSR), one core like the reference
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        adj, scale = cpu_sample_graph(args.workload, 12.0, k_max, f, dev)
-        t_cpu = time_oracle(adj, k_max, scales, f)
-        cpu_baseline = {"value": adj.nnz * k_max * f / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                        "host_cores": os.cpu_count(), "seconds": t_cpu,
-                        "sample": (f"{args.workload}-shape generator at scale {scale:.4f} (N={adj.shape[0]}, "
-                                   f"nnz={adj.nnz}), same K/S/F; oracle port of calibration/WATS.py:39-74 "
-                                   "(scipy, single-threaded like the reference), one run")}
+        import scipy.sparse as sp
+        adj = sp.csr_matrix((np.ones(nnz, np.float32), graph.colidx.cpu().numpy(), graph.rowptr.cpu().numpy()), shape=(n, n))
+        if k_max * f > REFERENCE_FULL_GRAPH_LIMIT and nnz > 5_000_000:
+            cpu_baseline = {"skipped": "wide signal on a large graph: run `bench.py --impl reference` (bounded sample)"}
+        else:
+            cpu_baseline = time_cpu_path(adj, k_max, scales, f, stock_runs=1, split_run=False)
 
-    # kernels of ours per step: SELL path = prescale + K x (SpMV + epilogue); wide path = padded prescale +
-    # K orders (+ L1 normalisation when the row spans several feature tiles); narrow generic = prescale + K
-    if kernel_name == "sell_spmv_kernel":
-        launches_per_step = 1 + 2 * k_max
-    elif f >= 8:
-        launches_per_step = 1 + k_max + (1 if (f + 3) // 4 * 4 > 128 else 0)
-    else:
-        launches_per_step = k_max + (1 if f <= 4 else 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}-shape", "n": n, "nnz": nnz, "k": k_max, "scales": n_scales, "f": f,
-                   "self_loops": True, "parallelism": "1 GPU", "ugca_flips": int(args.flips),
-                   "cuda_graph": session is not None, "event_stride": EV_STRIDE, "l2_policy": (
-                       "inputs larger than L2 (CSR %.0f MB vs 126 MB L2), no flush" % (4 * nnz / 1e6)
-                       if 4 * nnz > 126e6 else "inputs fit in L2: latency-bound configuration, no flush")},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "config": workload_config(args.workload, n, nnz, k_max, n_scales, f, args.flips),
+        "run": {"parallelism": "1 GPU", "path": "sell-step" if narrow else ("wide" if f >= 8 else "csr-generic"),
+                "cuda_graph": session is not None, "event_stride": EV_STRIDE},
+        "roofline": roofline, "roofline_wide": roofline_wide, "ugca": ugca, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": sampler.summary(),
     }
@@ -424,12 +671,7 @@ def run_replicas(args, rank, local_rank, world):
     nnz = graph.nnz
     x0 = None if f == 1 else torch.randn(n, f, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
     budget = args.flips or 5
-    gen = torch.Generator().manual_seed(1000 + rank)
-    cands = []
-    for _ in range(args.steps + max(3, args.warmup)):
-        picks = torch.randint(0, n, (budget + 1,), generator=gen).tolist()
-        t, others = picks[0], [j for j in picks[1:] if j != picks[0]]
-        cands.append(([t] * len(others) + others, others + [t] * len(others), [1.0] * (2 * len(others))))
+    cands = [make_flips(n, budget, 1000 * (rank + 1) + i) for i in range(args.steps + max(3, args.warmup))]
     it = iter(cands)
     for _ in range(max(3, args.warmup)):
         egnn.graph_wavelet_features(graph, k=k_max, s=scales, X0=x0, deltas=next(it))
@@ -455,12 +697,11 @@ def run_replicas(args, rank, local_rank, world):
             "metric": METRIC, "value": work / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-shape", "n": n, "nnz": nnz, "k": k_max, "scales": n_scales, "f": f,
-                       "self_loops": True, "ugca_flips": budget,
-                       "parallelism": f"{world} replicas: whole graph per GPU, one perturbation candidate per rank "
-                                      "per step, no exchange"},
+            "config": workload_config(args.workload, n, nnz, k_max, n_scales, f, budget),
+            "run": {"parallelism": f"{world} replicas: whole graph per GPU, one perturbation candidate per rank "
+                                   "per step, no exchange"},
             "roofline": None, "cpu_baseline": None, "e2e": None,
-            "gpu_launches": int((1 + 2 * k_max + 1) * args.steps * world), "clocks": sampler.summary(),
+            "gpu_launches": int(5 * args.steps * world), "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

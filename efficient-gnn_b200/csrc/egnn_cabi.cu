@@ -502,7 +502,8 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
                       const int32_t* delta_row_host, const int32_t* delta_col_host,
                       const float* delta_val_host, int32_t n_delta, void* workspace,
                       size_t workspace_bytes, egnn_stream_t stream, void* const* order_events_host,
-                      const egnn_sell_plan* sell_plan, const int32_t* row_order_or_null) {
+                      const egnn_sell_plan* sell_plan, const int32_t* row_order_or_null,
+                      const float* y0_or_null) {
     EGNN_REQUIRE(rowptr && dinv && iso && x0 && out && coeffs_host, "null pointer");
     EGNN_REQUIRE(nnz == 0 || colidx, "null colidx");
     EGNN_REQUIRE(n >= 0 && n < (int64_t(1) << 31) && nnz >= 0 && nnz < (int64_t(1) << 31), "n/nnz out of int32 range");
@@ -564,7 +565,8 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
         SellStepParams sp{};
         step_fill_plan(sp, sell_plan);
         sp.delta = p.delta;
-        sp.dinv = dinv; sp.iso = iso; sp.x0 = x0; sp.operand_first = nullptr;
+        sp.dinv = dinv; sp.iso = iso; sp.x0 = x0;
+        sp.operand_first = y0_or_null;       // dinv (.) T_0 kept by the caller (fixed per graph for the default signal)
         sp.operand[0] = ybuf[0]; sp.operand[1] = ybuf[1];
         sp.ydst[0][0] = ybuf[0]; sp.ydst[1][0] = ybuf[1]; sp.n_dst = 1;
         sp.tbuf[0] = tbuf[0]; sp.tbuf[1] = tbuf[1]; sp.t_all = t_all_or_null; sp.out = out;

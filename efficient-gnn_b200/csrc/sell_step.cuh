@@ -411,6 +411,8 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
         }
         bar_arrive(false);                                     // this CTA's partial sums are in place; shared memory is free
         trace();
+        // (measured and dropped: prefetching the head of the next order's index stream into L2
+        // while HBM idles here made the step slower for every amount tried)
 
         // ================= epilogue phase: the CTA's own rows ================================
         // the row's own operands are requested before the wait for everybody's partial sums

@@ -195,6 +195,7 @@ class CsrGraph:
         self._sell_structural = False   # the False above is final (weighted / unsorted / empty), not a threshold
         self.narrow_calls = 0      # F = 1 passes run on this graph (the plan is built on the second)
         self._row_order = None     # lazily built processing order of the wide kernel
+        self._y0 = None            # lazily built dinv * x0 (first operand of the narrow path, default signal)
 
     def _release_scratch(self):
         self._diag = self._colsum = None
@@ -208,6 +209,18 @@ class CsrGraph:
                                             _cabi.ptr(self._colsum), _cabi.ptr(self._unsorted_flag), _stream()),
                         "egnn_graph_prep")
         self._release_scratch()
+
+    def y0(self):
+        """``dinv * x0`` of the default signal: the first gather operand of the
+        narrow path, fixed per graph (one small kernel on first use)."""
+        if self._y0 is None:
+            with torch.cuda.device(self.device):
+                y = torch.empty(max(1, self.n), dtype=torch.float32, device=self.device)
+                if self.n:
+                    _cabi.check(_cabi.load().egnn_prescale(_cabi.ptr(self.x0), _cabi.ptr(self.dinv), _cabi.ptr(y), self.n, 1, 0,
+                                                           _stream()), "egnn_prescale")
+            self._y0 = y
+        return self._y0
 
     # -- processing order for the wide (F >= 8) kernel ----------------------------
     def row_order(self):

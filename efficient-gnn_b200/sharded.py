@@ -584,7 +584,7 @@ class ShardedWavelet:
 # bench.py entry for N > 1 (launched by torch.distributed.run)                   #
 # --------------------------------------------------------------------------- #
 def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, clock_sampler_cls,
-                physical_gpu_index, scale_list):
+                physical_gpu_index, scale_list, workload_config, make_flips):
     from . import synth
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -630,6 +630,7 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
         torch.cuda.synchronize()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    dist.barrier()
     start.record()
     for _ in range(args.steps):
         step()
@@ -643,9 +644,34 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
     ms_per_step = float(ms.item())
     peer_error = sw.exchange_error()
 
-    # optional self-check: every rank also runs the single-GPU path on the whole graph
+    # UGCA per-perturbation recompute on the SHARDED graph (BASELINE config 5): the same global flip
+    # list on every rank, applied on top of the shards' plans; device-timed, max over ranks
+    ugca = None
+    if f == 1 and not getattr(args, "no_ugca", False):
+        budget = 5
+        cands = [make_flips(n, budget, 100 + i) for i in range(32)]
+        for i in range(3):
+            sw.features(k=k_max, s=scales, deltas=cands[i])
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        u_steps = 64
+        for i in range(u_steps):
+            sw.features(k=k_max, s=scales, deltas=cands[i % len(cands)])
+        b.record()
+        torch.cuda.synchronize()
+        u_ms = torch.tensor([a.elapsed_time(b) / u_steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(u_ms, op=dist.ReduceOp.MAX)
+        ugca = {"flips": budget, "recompute_ms": float(u_ms.item()), "value": work / (float(u_ms.item()) * 1e-3),
+                "unperturbed_ms": ms_per_step, "steps": u_steps,
+                "entry": "ShardedWavelet.features(deltas=(rows, cols, vals)) on every rank: replicated degree patch + "
+                         "one step kernel per rank with the flips as kernel arguments; eager launches"}
+        peer_error |= sw.exchange_error()
+
+    # self-check (outside the timed region): every rank also runs the single-GPU path on the whole graph
     check = None
-    if getattr(args, "check", False):
+    if not getattr(args, "no_check", False):
         from .graph import CsrGraph
         from .wats import graph_wavelet_features
         rp_full, ci_full, _ = synth.synth_csr(args.workload, self_loops=True, device=dev)
@@ -653,12 +679,22 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
         x_full = None
         if f > 1:
             x_full = torch.randn(n, f, device=dev, generator=torch.Generator(device=dev).manual_seed(sh.seed))
-        want = graph_wavelet_features(gfull, k=k_max, s=scales, X0=x_full)[sw.row_begin:sw.row_end]
-        got = session().clone()
+        want = graph_wavelet_features(gfull, k=k_max, s=scales, X0=x_full, normalize=False)[sw.row_begin:sw.row_end]
+        got = sw.features(k=k_max, s=scales, X0_local=x0, normalize=False)
+        scale_ref = torch.tensor([float(want.abs().max().item()) if sw.rows else 0.0], device=dev, dtype=torch.float64)
         diff = torch.tensor([float((got - want).abs().max().item()) if sw.rows else 0.0], device=dev,
                             dtype=torch.float64)
         dist.all_reduce(diff, op=dist.ReduceOp.MAX)
-        check = {"max_abs_diff_vs_single_gpu": float(diff.item())}
+        dist.all_reduce(scale_ref, op=dist.ReduceOp.MAX)
+        check = {"max_abs_diff_vs_single_gpu": float(diff.item()), "max_abs_single_gpu": float(scale_ref.item()),
+                 "quantity": "un-normalised combination S of every rank's rows (the normalised F=1 feature is sign(S))"}
+        if ugca is not None:          # and the sharded recompute against the single-GPU recompute of the same flips
+            want_d = graph_wavelet_features(gfull, k=k_max, s=scales, deltas=cands[0], normalize=False)[sw.row_begin:sw.row_end]
+            got_d = sw.features(k=k_max, s=scales, deltas=cands[0], normalize=False)
+            dd = torch.tensor([float((got_d - want_d).abs().max().item()) if sw.rows else 0.0], device=dev,
+                              dtype=torch.float64)
+            dist.all_reduce(dd, op=dist.ReduceOp.MAX)
+            check["ugca_max_abs_diff_vs_single_gpu"] = float(dd.item())
         del gfull, rp_full, ci_full, want, got
 
     # end to end: pinned host shard -> device -> features -> host, every step
@@ -702,27 +738,36 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
         b_k = algorithmic_bytes(n, nnz, f, k_max, n_scales)
         peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
         peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.isfile(peaks) else 6650.0
-        achieved = sum(b_k) / (ms_per_step * 1e-3) / 1e9          # whole step, all ranks: aggregate GB/s
+        narrow = sw.plan is not None and f == 1
+        fused = (sw.peer is not None and f == 1) or (sw.fused_wide and f >= WIDE_MIN_F)
+        if narrow:                    # the kernel's own stream (2-byte indices), summed over the ranks' plans
+            own = 2 * sw.plan.n_entries + 4 * (sw.plan.n_slices + 1) + 4 * sw.plan.n_vrows + 8 * sw.plan.n_rowv
+            own = float(own) * world * k_max          # shards are statistically equal: rank 0's plan x world
+            achieved = own / (ms_per_step * 1e-3) / 1e9
+            model = "own stream of the step kernels (rank 0's plan x ranks x K), whole step incl. exchange"
+        else:
+            achieved = sum(b_k) / (ms_per_step * 1e-3) / 1e9
+            model = "SURVEY 8d contract bytes, whole step incl. exchange"
         line = {
             "metric": metric, "value": work / (ms_per_step * 1e-3), "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-shape", "n": n, "nnz": nnz, "k": k_max, "scales": n_scales,
-                       "f": f, "self_loops": True,
-                       "parallelism": (f"{world} row shards, operand pushed into peer windows over NVLink by the "
-                                       "epilogue kernel, flag wait in the next SpMV (no collective launch)"
-                                       if ((sw.peer is not None and f == 1) or (sw.fused_wide and f >= WIDE_MIN_F)) else
-                                       f"{world} row shards, all_gather of the order operand per order (NCCL)"),
-                       "path": ("sell-f1" if (sw.plan is not None and f == 1) else
-                                "wide-fused" if (sw.fused_wide and f >= WIDE_MIN_F) else "csr-split-overlap"),
-                       "exchange": ("peer-window" if ((sw.peer is not None and f == 1) or
-                                                      (sw.fused_wide and f >= WIDE_MIN_F)) else "nccl-allgather"),
-                       "cuda_graph": bool(use_graph),
-                       "l2_policy": "per-rank CSR shard %.0f MB; no flush" % (4 * nnz / world / 1e6)},
+            "config": workload_config(args.workload, n, nnz, k_max, n_scales, f, 0),
+            "run": {"parallelism": (f"{world} row shards; one persistent step kernel per rank: the epilogue stores the "
+                                    "next operand into every rank's window over NVLink, one CTA raises the flags, the "
+                                    "next order waits per column block on the ranks that own it (no collective launch)"
+                                    if (fused and narrow) else
+                                    f"{world} row shards, operand pushed into peer windows over NVLink by the epilogue, "
+                                    "flag wait in the next order's kernel (no collective launch)" if fused else
+                                    f"{world} row shards, all_gather of the order operand per order (NCCL)"),
+                    "path": ("sell-step" if narrow else "wide-fused" if (sw.fused_wide and f >= WIDE_MIN_F)
+                             else "csr-split-overlap"),
+                    "exchange": "peer-window" if fused else "nccl-allgather", "cuda_graph": bool(use_graph),
+                    "per_rank_index_stream_mb": (2 * sw.plan.n_entries / 1e6) if narrow else 4 * nnz / world / 1e6},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None,
-                         "note": "whole step incl. exchange, aggregate over ranks, compulsory-bytes model"},
-            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()),
+                         "achieved_contract": sum(b_k) / (ms_per_step * 1e-3) / 1e9, "bytes_model": model},
+            "ugca": ugca, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()),
             "exchange_error": int(peer_error), "check": check,
             "clocks": sampler.summary(),
         }

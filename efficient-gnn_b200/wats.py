@@ -55,8 +55,10 @@ class WaveletResult:
 
 def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_scale: float,
               op_shift: float, normalize: bool, want_orders: bool, deltas=None,
-              degree_vectors=None, order_events=None, use_sell=None):
-    """One call of egnn_cheb_wavelet.  Returns (out [N,S,F], t_all or None)."""
+              degree_vectors=None, order_events=None, use_sell=None, default_signal=False):
+    """One call of egnn_cheb_wavelet.  Returns (out [N,S,F], t_all or None).
+    ``default_signal``: x0 is the graph's own log1p(degree) with its own degree
+    vectors, so the first operand dinv * x0 is the one cached on the graph."""
     lib = _cabi.load()
     n, dev = graph.n, graph.device
     if x0.dim() == 1:
@@ -94,7 +96,8 @@ def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_
             _cabi.host_array(C.c_int32, [int(v) for v in d_cols]),
             _cabi.host_array(C.c_float, [float(v) for v in d_vals]), len(d_rows),
             _cabi.ptr(ws), ws_bytes, _stream(), order_events,
-            None if plan is None else C.byref(plan), _cabi.ptr(row_order)), "egnn_cheb_wavelet")
+            None if plan is None else C.byref(plan), _cabi.ptr(row_order),
+            _cabi.ptr(graph.y0()) if (plan is not None and default_signal) else None), "egnn_cheb_wavelet")
     return out, t_all
 
 
@@ -203,14 +206,15 @@ def graph_wavelet_features(adj_matrix, k=3, s=0.8, *, X0=None, lambda_max: float
     else:
         deltas = None
     op_scale = 2.0 / float(lambda_max)
+    default_signal = X0 is None and deltas is None
     if return_parts:
         comb, t_all = _run_cheb(graph, x0, k, coeffs, op_scale, -1.0, False, True, deltas, degree_vectors,
-                                use_sell=_use_sell)
+                                use_sell=_use_sell, default_signal=default_signal)
         feats = comb / (comb.abs().sum(dim=2, keepdim=True) + 1e-8) if normalize else comb
         feats = feats.reshape(graph.n, -1)
         return WaveletResult(feats, [t_all[i] for i in range(k + 1)], comb)
     out, _ = _run_cheb(graph, x0, k, coeffs, op_scale, -1.0, normalize, False, deltas, degree_vectors,
-                       _order_events, _use_sell)
+                       _order_events, _use_sell, default_signal)
     return out.reshape(graph.n, -1)
 
 

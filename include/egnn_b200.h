@@ -187,11 +187,15 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
  * workspace: egnn_cheb_workspace_bytes(n, f) bytes, 256-byte aligned.
  * order_events_host: NULL, or 2*K cudaEvent_t handles; events 2(k-1) and
  * 2(k-1)+1 are recorded on `stream` around order k's kernel (per-kernel
- * timing for the roofline report; no effect on results).
+ * timing for the roofline report; no effect on results).  With a SELL plan the
+ * whole step is one launch: events 0 and 1 bracket it, the rest follow it.
  * sell_plan_or_null: when given (f == 1, binary adjacency) the orders run on
  * the SELL plan; rowptr/colidx are then only used for the argument checks.
  * row_order_or_null: the processing order from egnn_row_order (used for
- * f >= 8: longest rows first, hub rows summed by a whole CTA); NULL = CSR order. */
+ * f >= 8: longest rows first, hub rows summed by a whole CTA); NULL = CSR order.
+ * y0_or_null (SELL plan only): dinv (.) x0 [n] when the caller already holds it
+ * (fixed per graph for the default signal log1p(degree)): the step kernel then
+ * skips computing it.  Must match dinv and x0 (so not with edge flips).        */
 size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f);
 int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx,
                       const float* vals_or_null, const float* dinv,
@@ -203,7 +207,8 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx,
                       const float* delta_val_host, int32_t n_delta,
                       void* workspace, size_t workspace_bytes,
                       egnn_stream_t stream, void* const* order_events_host,
-                      const egnn_sell_plan* sell_plan_or_null, const int32_t* row_order_or_null);
+                      const egnn_sell_plan* sell_plan_or_null, const int32_t* row_order_or_null,
+                      const float* y0_or_null);
 
 /* Processing order of the wide-signal kernel (new in this build): rows by
  * descending stored-entry count.  order_out: int32[n + 1] - the permutation,

@@ -4,12 +4,14 @@ this path from the sources where they lie under ``/root/reference``.
 TEST INFRASTRUCTURE ONLY (like everything under ``oracle/``).
 
 The reference is pure Python, so its "build" is ``py_compile``: each module is
-compiled, unmodified, straight from ``/root/reference/<path>.py`` into a
-sourceless ``oracle/_ref/<path>.pyc``.  No reference source enters the repo;
-``oracle/_ref/`` is git-ignored but not gpurun-ignored, so the compiled
-modules travel to the GPU box (same image, same interpreter) where
-``/root/reference`` does not exist.  ``oracle/ref_shim.py`` imports them there
-so that
+compiled, unmodified, straight from ``/root/reference/<path>.py`` into
+``oracle/_ref/<path>.bin`` - the bytes of a ``.pyc`` file under another
+extension, because the snapshot that travels to the GPU box leaves ``*.pyc``
+behind (probed: ``.bin`` travels, like the built ``.so``).  No reference source
+enters the repo; ``oracle/_ref/`` is git-ignored but not gpurun-ignored, so the
+compiled modules reach the GPU box (same image, same interpreter) where
+``/root/reference`` does not exist.  ``oracle/ref_shim.py`` loads them there
+(marshal -> code object -> module) so that
 
 * ``tests/test_gpu_reference_class.py`` runs the *reference's* ``WATS`` class
   (calibration/WATS.py:76-170) with only ``graph_wavelet_features`` swapped,
@@ -45,7 +47,7 @@ def build(verbose: bool = True) -> bool:
         return False
     for rel in MODULES:
         src = os.path.join(REFERENCE_ROOT, rel)
-        dst = os.path.join(OUT, os.path.splitext(rel)[0] + ".pyc")
+        dst = os.path.join(OUT, os.path.splitext(rel)[0] + ".bin")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         # dfile keeps the reference path in tracebacks; unchecked-hash pyc needs no source beside it
         py_compile.compile(src, cfile=dst, dfile=src, doraise=True,

@@ -6,7 +6,8 @@ Two places can hold them:
 * ``/root/reference`` - the reference checkout, mounted in the build container
   only;
 * ``oracle/_ref/`` - the same modules byte-compiled by ``oracle/build_ref.py``
-  (sourceless ``.pyc``, git-ignored, travels to the GPU box with the snapshot).
+  (``.pyc`` bytes in ``.bin`` files - the snapshot drops ``*.pyc`` - git-ignored,
+  travels to the GPU box with the snapshot).
 
 A plain ``import calibration.WATS`` fails because the package ``__init__``
 pulls matplotlib (calibration/__init__.py:20 -> TS.py:17) and
@@ -17,6 +18,7 @@ the plotting libraries, then import the three files the path needs.
 from __future__ import annotations
 
 import importlib
+import marshal
 import os
 import sys
 import types
@@ -36,7 +38,7 @@ def reference_available() -> bool:
 
 def staged_available() -> bool:
     """``oracle/_ref`` holds the byte-compiled reference modules."""
-    return _has(STAGED_ROOT, ".pyc")
+    return _has(STAGED_ROOT, ".bin")
 
 
 def reference_root():
@@ -73,6 +75,24 @@ def load_reference(root=None):
             mod.__egnn_shim__ = root
             sys.modules[pkg] = mod
     importlib.invalidate_caches()
+    if root == STAGED_ROOT:
+        # byte-compiled modules: unmarshal the code object and run it in a module registered
+        # under the reference's own dotted name (dependencies first, so that the relative
+        # import in calibration/WATS.py:7 finds calibration.utils in sys.modules)
+        for name in ("calibration.utils", "calibration.WATS", "src.gnn.model", "utils.ece"):
+            if name in sys.modules and getattr(sys.modules[name], "__egnn_shim__", None) == root:
+                continue
+            path = os.path.join(root, *name.split(".")) + ".bin"
+            with open(path, "rb") as fh:
+                code = marshal.loads(fh.read()[16:])           # 16-byte pyc header, then the code object
+            mod = types.ModuleType(name)
+            mod.__file__ = path
+            mod.__package__ = name.rpartition(".")[0]
+            mod.__egnn_shim__ = root
+            sys.modules[name] = mod
+            exec(code, mod.__dict__)
+            setattr(sys.modules[mod.__package__], name.rpartition(".")[2], mod)
+        return sys.modules["calibration.WATS"], sys.modules["src.gnn.model"], sys.modules["utils.ece"]
     wats = importlib.import_module("calibration.WATS")
     model = importlib.import_module("src.gnn.model")
     ece = importlib.import_module("utils.ece")

@@ -17,9 +17,19 @@ def test_reference_arm_prints_the_contract_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["steps"] == 2
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    # the reference's own code when oracle/_ref is staged (or /root/reference is mounted), else the port
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+    want_kind = "reference" if ref_shim.reference_root() is not None else "port"
+    assert line["cpu_baseline"]["kind"] == want_kind and line["cpu_baseline"]["cores"] == 1
+    split = line["cpu_baseline"]["split_seconds"]
+    assert split["total"] > 0 and ("laplacian" in split or "laplacian_and_rescale" in split) and "recurrence" in split
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
-    assert line["config"]["workload"] == "cora-shape"
+    # same configuration object as the GPU arm prints: the full named shape, not a sample
+    from efficient_gnn_b200 import synth
+    cfg = line["config"]
+    assert cfg["workload"] == "cora-shape" and cfg["n"] == synth.SHAPES["cora"].n and cfg["k"] == 3 and cfg["f"] == 1
+    assert cfg["nnz"] == synth.SHAPES["cora"].nnz + cfg["n"] and line["scaling"] == "strong"
 
 
 def test_reference_arm_other_ranks_exit_quietly():
