@@ -261,6 +261,7 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
     int stamp_i = 1;
     bool waited_first = false;                                 // before the first store into the peers' windows
     bool pending = false, pending_signal = false;              // a barrier this CTA has arrived at but not yet waited for
+    const bool late_done = PEER && p.delta.n > 0;              // the last epilogue reads the window (edge-flip corrections)
     __syncthreads();
 
     // the peers may still be reading the buffers of the previous step: wait until every one of
@@ -370,6 +371,7 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
                         bulk_g2s(ysm + o, src + o, (unsigned)min(kStageChunkFloats, cnt4 - o) * 4u, &stage_bar);
                 }
             }
+            if (PEER && !held) __syncthreads();                // nobody touches the operand before the owners' flags are in
             if (tid >= 32) {                                   // warp 0 is busy issuing; the others fill the rest
                 for (int t = cnt4 + tid - 32; t < p.CB + kSellZeroSlots; t += kSellThreads - 32)
                     ysm[t] = t < cnt ? __ldcg(src + t) : 0.f;
@@ -427,7 +429,9 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
         if (i_b < r1) pre_b = step_row_prefetch(p, v, i_b);
         bar_wait();                                            // every partial sum of every row is in place
         stamp();
-        if (PEER && v.last) signal_peers();                    // nobody reads the windows any more in this step
+        // end-of-step signal: nobody reads the windows any more - unless edge flips are applied,
+        // whose corrections the last epilogue still reads from the operand (signalled after it)
+        if (PEER && v.last && !late_done) signal_peers();
         if (g == 0 && tid < p.C) p.sched[tid * kSellCtrStride] = (unsigned)__ldg(p.cta_info + 2 * p.n_cta + tid);   // counters for the next SpMV phase
         if (v.push) wait_first();
         for (int i = i_a; i < r1; i += kSellThreads) {
@@ -450,9 +454,9 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
             if (lane == 0) step_epilogue_finish(p, v, i, r, a);
         }
         // the next order (or a peer) reads what this phase wrote
-        if (k < p.order_end || (PEER && v.push)) {
+        if (k < p.order_end || (PEER && (v.push || (v.last && late_done)))) {
             bar_arrive(PEER && v.push);
-            pending = true; pending_signal = v.push;
+            pending = true; pending_signal = v.push || (v.last && late_done);
         }
         trace();                                               // this CTA's rows are done
     }

@@ -112,6 +112,46 @@ def test_two_rank_fused_exchange_matches_oracle(tmp_path, k, scales, f, steps, f
         assert np.array_equal(z["fused"][0], z["fused"][-1])           # deterministic across steps
 
 
+def _alternating_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        rp, ci, n = synth.synth_csr(SHAPE, self_loops=True)
+        assert n % 4 != 0                             # the last column block ends in a partial 16-byte group
+        part = sharded.RowPartition(n, world)
+        rpl, cil = part.slice_csr(rp, ci, rank)
+        sw = sharded.ShardedWavelet(rpl.to(dev), cil.to(dev), n, device=dev)
+        x_full = np.random.default_rng(5).standard_normal((n, 1)).astype(np.float32)
+        x = torch.from_numpy(x_full[sw.row_begin:sw.row_end]).to(dev)
+        bad = 0
+        for k in (3, 4):
+            base = sw.features(k=k, s=0.8, X0_local=x, normalize=False).clone()
+            for step in range(10):                    # every step stages different operand values
+                scale = float(2 ** (step % 3 + 1))
+                got = sw.features(k=k, s=0.8, X0_local=scale * x, normalize=False)
+                bad += int(not torch.equal(got, scale * base))      # scaling by a power of two is exact in float32
+        sw.check_exchange()
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as fh:
+            fh.write(str(bad))
+        sw.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_consecutive_steps_never_see_stale_operands(tmp_path):
+    """Steps whose operands differ (a power-of-two multiple of the same signal: results must be
+    the exact multiple): any element staged before its owner's flag arrived - e.g. the last,
+    partial 16-byte group of a column block, which is not part of the bulk copy - shows up."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (one process per GPU)")
+    import torch.multiprocessing as mp
+    mp.spawn(_alternating_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"rank{r}.txt").read() for r in range(2)] == ["0", "0"]
+
+
 def test_single_rank_window_is_a_plain_store(tmp_path):
     """world == 1: same kernels, no peers, no waits - must equal the NCCL-free path."""
     import torch.distributed as dist
