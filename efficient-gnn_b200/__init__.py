@@ -13,6 +13,7 @@ from . import _cabi  # noqa: F401
 from ._cabi import EgnnError  # noqa: F401
 from .graph import CsrGraph, as_graph  # noqa: F401
 from .metrics import calibration_metrics  # noqa: F401
+from .surrogate import SparseGCNSurrogate, StructureGradient  # noqa: F401
 from .wats import (  # noqa: F401
     WATS,
     LaplacianOperator,

@@ -29,6 +29,10 @@ SYMBOLS = {
     "egnn_calibration_metrics_ws_bytes": (_SZ, [_I32, _I32]),
     "egnn_calibration_metrics": (C.c_int, [_P, _I32, _P, _P, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     "egnn_temperature_head": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P]),
+    "egnn_gcn_propagate": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _I32, _P]),
+    "egnn_gcn_target_logits": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P]),
+    "egnn_gcn_structure_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _I32, _P, _P,
+                                          _P, _P, _P, _I32, _P]),
     "egnn_sell_geometry": (C.c_int, [_I64, _I64, _P, _P, _P]),
     "egnn_sell_ws_bytes": (_SZ, [_I64, _I64, _I32, _I32]),
     "egnn_sell_prepare": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _SZ, _P]),

@@ -12,6 +12,7 @@
 #include "prep.cuh"
 #include "sell.cuh"
 #include "sell_step.cuh"
+#include "surrogate.cuh"
 #include "wide.cuh"
 
 namespace egnn {
@@ -1153,6 +1154,90 @@ int egnn_graph_prep_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
         logdeg_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, st>>>(rowsum_local, n_rows, x0_local);
         EGNN_LAUNCH_CHECK("logdeg_kernel launch");
     }
+    return EGNN_OK;
+}
+
+// ---- sparse structure-gradient surrogate (surrogate.cuh) -------------------------
+static int gcn_check(const int32_t* rowptr, int64_t n, int32_t h) {
+    EGNN_REQUIRE(rowptr != nullptr, "null rowptr");
+    EGNN_REQUIRE(n >= 1 && n < (int64_t(1) << 31), "n out of range");
+    EGNN_REQUIRE(h >= 4 && h <= kGcnMaxHidden && h % 4 == 0, "hidden width must be a multiple of 4 in [4, 128]");
+    return EGNN_OK;
+}
+
+int egnn_gcn_propagate(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null, const float* m,
+                       const float* bias_or_null, float* y, float* deg_out_or_null, int64_t n, int32_t h,
+                       const int32_t* delta_row_host, const int32_t* delta_col_host, const float* delta_val_host,
+                       int32_t n_delta, egnn_stream_t stream) {
+    int rc = gcn_check(rowptr, n, h);
+    if (rc) return rc;
+    EGNN_REQUIRE(m && y, "null pointer");
+    DeltaList d;
+    rc = fill_delta(d, delta_row_host, delta_col_host, delta_val_host, n_delta);
+    if (rc) return rc;
+    for (int i = 0; i < n_delta; ++i)
+        EGNN_REQUIRE(d.row[i] >= 0 && d.row[i] < n && d.col[i] >= 0 && d.col[i] < n, "delta index out of range");
+    const unsigned grid = (unsigned)ceil_div64(n * 32, 256);
+    if (vals_or_null)
+        gcn_propagate_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, colidx, vals_or_null, m, bias_or_null, y,
+                                                                           deg_out_or_null, n, h, d);
+    else
+        gcn_propagate_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, colidx, nullptr, m, bias_or_null, y,
+                                                                            deg_out_or_null, n, h, d);
+    EGNN_LAUNCH_CHECK("gcn_propagate_kernel launch");
+    return EGNN_OK;
+}
+
+int egnn_gcn_target_logits(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null, const float* z1,
+                           const float* w2, const float* b2, int32_t target, int64_t n, int32_t h, int32_t n_classes,
+                           float* logits_out, float* ctx, const int32_t* delta_row_host, const int32_t* delta_col_host,
+                           const float* delta_val_host, int32_t n_delta, egnn_stream_t stream) {
+    int rc = gcn_check(rowptr, n, h);
+    if (rc) return rc;
+    EGNN_REQUIRE(z1 && w2 && b2 && logits_out && ctx, "null pointer");
+    EGNN_REQUIRE(target >= 0 && target < n && n_classes >= 1, "bad target / classes");
+    DeltaList d;
+    rc = fill_delta(d, delta_row_host, delta_col_host, delta_val_host, n_delta);
+    if (rc) return rc;
+    for (int i = 0; i < n_delta; ++i)
+        EGNN_REQUIRE(d.row[i] >= 0 && d.row[i] < n && d.col[i] >= 0 && d.col[i] < n, "delta index out of range");
+    if (vals_or_null)
+        gcn_target_logits_kernel<true><<<1, 256, 0, (cudaStream_t)stream>>>(rowptr, colidx, vals_or_null, z1, w2, b2, target, h,
+                                                                            n_classes, logits_out, ctx, d);
+    else
+        gcn_target_logits_kernel<false><<<1, 256, 0, (cudaStream_t)stream>>>(rowptr, colidx, nullptr, z1, w2, b2, target, h,
+                                                                             n_classes, logits_out, ctx, d);
+    EGNN_LAUNCH_CHECK("gcn_target_logits_kernel launch");
+    return EGNN_OK;
+}
+
+int egnn_gcn_structure_grad(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null,
+                            const float* upstream, const float* w2, const float* z1, const float* xw, const float* b1,
+                            const float* deg, const float* ctx, int32_t target, int64_t n, int32_t h, int32_t n_classes,
+                            float* grad_row, float* grad_col, const int32_t* delta_row_host,
+                            const int32_t* delta_col_host, const float* delta_val_host, int32_t n_delta,
+                            egnn_stream_t stream) {
+    int rc = gcn_check(rowptr, n, h);
+    if (rc) return rc;
+    EGNN_REQUIRE(upstream && w2 && z1 && xw && b1 && deg && ctx && grad_row && grad_col, "null pointer");
+    EGNN_REQUIRE(target >= 0 && target < n && n_classes >= 1, "bad target / classes");
+    DeltaList d;
+    rc = fill_delta(d, delta_row_host, delta_col_host, delta_val_host, n_delta);
+    if (rc) return rc;
+    for (int i = 0; i < n_delta; ++i)
+        EGNN_REQUIRE(d.row[i] >= 0 && d.row[i] < n && d.col[i] >= 0 && d.col[i] < n, "delta index out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = check_cuda(cudaMemsetAsync(grad_col, 0, sizeof(float) * n, st), "memset grad_col");
+    if (rc) return rc;
+    gcn_grad_row_kernel<<<grid_for(n * 8, 256), 256, 0, st>>>(upstream, w2, z1, xw, b1, ctx, target, n, h, n_classes, grad_row);
+    EGNN_LAUNCH_CHECK("gcn_grad_row_kernel launch");
+    if (vals_or_null)
+        gcn_grad_col_kernel<true><<<1, 256, 0, st>>>(rowptr, colidx, vals_or_null, upstream, w2, z1, xw, b1, deg, ctx, grad_row,
+                                                     target, h, n_classes, grad_col, d);
+    else
+        gcn_grad_col_kernel<false><<<1, 256, 0, st>>>(rowptr, colidx, nullptr, upstream, w2, z1, xw, b1, deg, ctx, grad_row,
+                                                      target, h, n_classes, grad_col, d);
+    EGNN_LAUNCH_CHECK("gcn_grad_col_kernel launch");
     return EGNN_OK;
 }
 

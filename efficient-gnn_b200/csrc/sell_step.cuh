@@ -236,8 +236,12 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
 
     const int c = __ldg(p.cta_info + g);                       // column block this CTA serves (-1: none)
     const int rank_in_block = __ldg(p.cta_info + p.n_cta + g);
-    int bs0 = 0, bs1 = 0;
-    if (c >= 0) { bs0 = __ldg(p.blk_slice_ptr + c); bs1 = __ldg(p.blk_slice_ptr + c + 1); }
+    int bs0 = 0, bs1 = 0, ctas_in_block = 1;
+    if (c >= 0) {
+        bs0 = __ldg(p.blk_slice_ptr + c);
+        bs1 = __ldg(p.blk_slice_ptr + c + 1);
+        ctas_in_block = __ldg(p.cta_info + 2 * p.n_cta + c) / (kSellThreads / 32);
+    }
     const bool has_slices = c >= 0 && bs1 > bs0;
     const int col0 = c >= 0 ? c * p.CB : 0;
     const int cnt = c >= 0 ? min(p.CB, p.n_cols - col0) : 0;
@@ -337,11 +341,13 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
 
         // ================= SpMV phase: slices of this CTA's column block ===================
         // what does not depend on the operand comes first: the warp's first slice is fixed
-        // (the block's counter starts at 32 x its CTAs), its metadata and the head of its index
+        // (warp w of the block's r-th CTA takes slice w * CTAs + r, so every CTA starts with the
+        // same mix of long and short ones - on a row shard these first slices are most of the
+        // work; the block's counter starts past them), its metadata and the head of its index
         // stream are requested while the previous phase's barrier completes
         int s = bs1, off = 0, end = 0, slot = -1;
         if (has_slices) {
-            s = bs0 + rank_in_block * kWarps + wid;
+            s = bs0 + wid * ctas_in_block + rank_in_block;
             if (s < bs1) {
                 off = __ldg(p.slice_off + s);
                 end = __ldg(p.slice_off + s + 1);

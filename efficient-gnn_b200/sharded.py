@@ -644,6 +644,30 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
     ms_per_step = float(ms.item())
     peer_error = sw.exchange_error()
 
+    # phase breakdown of one eager step from the kernel's own timestamps (rank 0's CTA 0, and the
+    # per-CTA trace reduced to min / mean / max), outside the timed region
+    phase_us = None
+    if sw.plan is not None and f == 1:
+        from .graph import enable_phase_stamps, read_phase_stamps
+        enable_phase_stamps(sw.plan, True, trace=True)
+        sw.features(k=k_max, s=scales)
+        torch.cuda.synchronize()
+        in_kernel_y0 = sw.peer is None or sw.y0_full is None
+        phase_us = read_phase_stamps(sw.plan, k_max, first_operand_in_kernel=in_kernel_y0)
+        st = sw.plan._keepalive["stamps"].cpu().numpy().astype(np.int64)
+        glob, per = st[:64], st[64:].reshape(sw.plan.n_cta, 64)
+        o0 = 1 if in_kernel_y0 else 0
+        trace = []
+        for order in range(1, k_max + 1):
+            opened = glob[o0 + 2 * (order - 1)]
+            stage, done, rows = (per[:, 3 * (order - 1) + j] - opened for j in range(3))
+            trace.append({"stage_done": [float(stage.min()) / 1e3, float(stage.mean()) / 1e3, float(stage.max()) / 1e3],
+                          "slices_done": [float(done.min()) / 1e3, float(done.mean()) / 1e3, float(done.max()) / 1e3],
+                          "rows_done": [float(rows.min()) / 1e3, float(rows.mean()) / 1e3, float(rows.max()) / 1e3]})
+        phase_us["per_cta_us_after_order_opened_min_mean_max"] = trace
+        enable_phase_stamps(sw.plan, False)
+        dist.barrier()
+
     # UGCA per-perturbation recompute on the SHARDED graph (BASELINE config 5): the same global flip
     # list on every rank, applied on top of the shards' plans; device-timed, max over ranks
     ugca = None
@@ -763,6 +787,7 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
                     "path": ("sell-step" if narrow else "wide-fused" if (sw.fused_wide and f >= WIDE_MIN_F)
                              else "csr-split-overlap"),
                     "exchange": "peer-window" if fused else "nccl-allgather", "cuda_graph": bool(use_graph),
+                    "phase_us_rank0": phase_us,
                     "per_rank_index_stream_mb": (2 * sw.plan.n_entries / 1e6) if narrow else 4 * nnz / world / 1e6},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None,

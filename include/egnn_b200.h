@@ -230,6 +230,38 @@ int egnn_temperature_head(const float* feats, const float* w1, const float* b1,
                           float* out, float* temps_out_or_null, int64_t n, int32_t f,
                           int32_t hidden, int32_t n_classes, egnn_stream_t stream);
 
+/* ---- sparse structure-gradient surrogate -----------------------
+ * What the UGCA attack needs from the calibrated surrogate, without the dense
+ * [N,N] forward / backward of calib_attack/calib_fga.py:864-890: the logits of
+ * ONE target node of the reference's two-layer row-normalised GCN
+ * (src/gnn/model.py:43-52: A_n = D^-1 A with deg 0 -> 1; Z1 = A_n X W1^T + b1;
+ * logits = (A_n relu(Z1)) W2^T + b2) on a CSR adjacency (+ edge flips), and row
+ * and column `target` of dLoss/dA - the only parts calib_fga.py:881 reads.
+ *   egnn_gcn_propagate      y = A_n m + bias (m = X W1^T [n,h], y = Z1), deg_out = raw row sums
+ *   egnn_gcn_target_logits  logits_out [n_classes] of node `target`; ctx (EGNN_GCN_CTX_FLOATS
+ *                           floats) carries (A_n relu(Z1))[target,:], deg and the diagonal entry
+ *   egnn_gcn_structure_grad grad_row[m] = dLoss/dA[target,m], grad_col[i] = dLoss/dA[i,target]
+ *                           for upstream = dLoss/dlogits[target,:] [n_classes] (device)
+ * h: hidden width, a multiple of 4 up to 128.  delta_*: flips as in egnn_cheb_wavelet
+ * (the same list must be passed to all three calls of one evaluation).        */
+#define EGNN_GCN_CTX_FLOATS 136
+int egnn_gcn_propagate(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null,
+                       const float* m, const float* bias_or_null, float* y, float* deg_out_or_null,
+                       int64_t n, int32_t h,
+                       const int32_t* delta_row_host, const int32_t* delta_col_host,
+                       const float* delta_val_host, int32_t n_delta, egnn_stream_t stream);
+int egnn_gcn_target_logits(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null,
+                           const float* z1, const float* w2, const float* b2, int32_t target,
+                           int64_t n, int32_t h, int32_t n_classes, float* logits_out, float* ctx,
+                           const int32_t* delta_row_host, const int32_t* delta_col_host,
+                           const float* delta_val_host, int32_t n_delta, egnn_stream_t stream);
+int egnn_gcn_structure_grad(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null,
+                            const float* upstream, const float* w2, const float* z1, const float* xw,
+                            const float* b1, const float* deg, const float* ctx, int32_t target,
+                            int64_t n, int32_t h, int32_t n_classes, float* grad_row, float* grad_col,
+                            const int32_t* delta_row_host, const int32_t* delta_col_host,
+                            const float* delta_val_host, int32_t n_delta, egnn_stream_t stream);
+
 /* ---- calibration metrics on the device --------------------------
  * The evaluation triple of benchmark_calibration_methods.py:100-127 on the
  * samples selected by mask_or_null (uint8 [n]; NULL = all): out3[0] accuracy,

@@ -1,19 +1,6 @@
-# multi-GPU: the 2-rank tests of the fused exchange (step kernel protocol), then the sharded bench at N GPUs
 N=${1:-2}
 mkdir -p gpurun_out
-if [ "$N" = "2" ]; then
 timeout 1500 python -m pytest tests/test_gpu_peer.py -x -q > gpurun_out/pytest_peer.log 2>&1; echo pytest-peer rc=$?
 tail -5 gpurun_out/pytest_peer.log
-fi
-for cfg in "--workload reddit" "--workload reddit --f 64" "--workload arxiv --f 128"; do
-tag=$(echo $cfg | tr -d ' -')
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 200 --warmup 10 $cfg > gpurun_out/bench_n${N}_$tag.log 2> gpurun_out/bench_n${N}_$tag.err; echo "bench N=$N $cfg rc=$?"
-python - <<PY
-import json
-try:
-    d=json.loads(open('gpurun_out/bench_n${N}_$tag.log').read().strip().splitlines()[-1])
-    print('ms/step', d['ms_per_step'], 'value', d['value'], 'frac', d['roofline']['frac'], 'check', d['check'], 'err', d['exchange_error'], 'ugca', (d.get('ugca') or {}).get('recompute_ms'), 'e2e ms', (d.get('e2e') or {}).get('ms_per_step'), d['run']['path'], d['run']['exchange'])
-except Exception as e:
-    print('parse failed', e); print(open('gpurun_out/bench_n${N}_$tag.err').read()[-1500:])
-PY
-done
+for i in 1 2; do python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 scripts/check_flips_sharded.py reddit 2>&1 | grep "rank 0\|Error\|error"; done
+bash scripts/gpu_r2_scale.sh $N
