@@ -28,6 +28,7 @@ void set_error(const char* fmt, ...) {
 
 static int device_sm_count();
 constexpr int kWideMinF = 8;             // narrower signals keep the multi-row-per-warp kernel (cheb.cuh)
+constexpr int kWideDynamicMaxDegree = 64;   // mean entries per row below which the wide kernel hands rows out dynamically
 
 static int pow2_ceil_log2(int64_t x) {
     int l = 0;
@@ -129,6 +130,9 @@ static int launch_wide_n(const WideParams& p, dim3 grid, cudaStream_t st) {
     return p.peer.world > 1 ? launch_wide_np<NZ_LOG2, true>(p, grid, st) : launch_wide_np<NZ_LOG2, false>(p, grid, st);
 }
 
+// (Measured and dropped: pinning the gather operand in L2 with an access-policy window and the
+// persisting set-aside - arxiv F = 128 0.283 -> 0.276 ms per order, Reddit F = 64 2.13 -> 2.28,
+// Physics F = 8415 2.77 -> 3.6: the set-aside shrinks the L2 left for the other four slabs.)
 // Wide kernel: persistent grid of kWideMinBlocks CTAs per SM per feature tile.
 static int launch_wide(const WideParams& p, const RingConfig& c, int sm_count, cudaStream_t st) {
     dim3 grid((unsigned)(sm_count * kWideMinBlocks), (unsigned)c.grid_y, 1);
@@ -493,7 +497,9 @@ size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f) {
     // f <= 4: two T slabs + two pre-scaled slabs; 4 < f < 8: two T slabs; f >= 8: two pre-scaled slabs
     const size_t width = f >= kWideMinF ? (size_t)((f + 3) / 4 * 4) : (size_t)f;     // wide slabs have 16-byte rows
     const size_t slab = align_up(sizeof(float) * (size_t)n * width, 256);
-    return slab * (f <= 4 ? 4 : 2) + 256;
+    // wide path: + one row counter per (order, feature tile) for the dynamic row schedule
+    const size_t counters = f >= kWideMinF ? align_up(sizeof(unsigned) * (size_t)EGNN_MAX_ORDER * (size_t)((width + 127) / 128), 256) : 0;
+    return slab * (f <= 4 ? 4 : 2) + counters + 256;
 }
 
 int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null,
@@ -601,12 +607,20 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
         wp.a = op_scale; wp.b = op_shift;
         prescale_pad_kernel<<<grid_for((int64_t)n * ldy, 256), 256, 0, st>>>(x0, dinv, yb[0], n, f, ldy, 0);
         EGNN_LAUNCH_CHECK("prescale_pad_kernel launch");
+        unsigned* counters = (unsigned*)(ws + 2 * yslab);          // [k][grid_y], zeroed once per call
+        rc = check_cuda(cudaMemsetAsync(counters, 0, sizeof(unsigned) * (size_t)k * (size_t)rcfg.grid_y, st), "memset row counters");
+        if (rc) return rc;
         const bool fuse_norm_w = normalize_l1 && rcfg.grid_y == 1;
         const int sms = device_sm_count();
         for (int order = 1; order <= k; ++order) {
             const bool last = order == k;
             wp.first = order == 1;
             wp.normalize = last && fuse_norm_w;
+            // dynamic rows pay off where rows are short and one feature tile covers the signal (arxiv
+            // shape F = 128: 0.283 -> 0.23 ms per order); measured slower on long rows (Reddit shape
+            // F = 64: 2.13 -> 2.48) and on many feature tiles (Physics F = 8415: 2.77 -> 3.3)
+            const bool dynamic_rows = rcfg.grid_y == 1 && nnz < (int64_t)kWideDynamicMaxDegree * n;
+            wp.row_counter = dynamic_rows ? counters + (size_t)(order - 1) * (size_t)rcfg.grid_y : nullptr;
             wp.ysrc = yb[(order - 1) & 1];
             wp.x0_own = order == 1 ? x0 : nullptr;
             wp.y2_own = order == 1 ? nullptr : yb[order & 1];

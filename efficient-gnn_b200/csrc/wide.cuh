@@ -53,6 +53,8 @@ struct WideParams {
     const float* vals;          // NULL: binary adjacency
     const int32_t* perm;        // processing order (degree-descending) or NULL: identity
     const int32_t* n_hub;       // device scalar: leading rows of perm summed by a whole CTA (NULL: none)
+    unsigned* row_counter;      // [gridDim.y] zeroed: rows of phase B are handed out dynamically, longest first
+                                // (NULL: dealt out cyclically - the sharded entry, which has no workspace)
     const float* dinv;          // [n_global]
     const uint8_t* iso;         // [n_global]
     const float* ysrc;          // dinv (.) T_{k-1}, [n_global, ldy], indexed by GLOBAL column
@@ -360,9 +362,19 @@ cheb_wide_kernel(const __grid_constant__ WideParams p) {
         }
     }
 
-    // ---- phase B: one row per warp, dealt out cyclically from the ordered rows --
+    // ---- phase B: one row per warp ---------------------------------------------------
+    // Rows are taken longest first.  Handing them out from a counter (greedy longest-processing-
+    // time schedule) matters on short-row graphs: dealt out cyclically, warp 0 gets the longest
+    // row of every round - on the arxiv shape (15 entries per row on average, 660 at most, 36
+    // rounds) the first warps carry twice the work of the last (ncu: slowest SM active 516 k
+    // cycles, average 364 k).  The row after next is requested while this one is summed, so the
+    // atomic's latency and the next row's pointer loads stay off the critical path.
     const int total_warps = gridDim.x * kWideWarps;
-    int r = n_hub + blockIdx.x * kWideWarps + wid;
+    unsigned* counter = p.row_counter ? p.row_counter + blockIdx.y : nullptr;
+    int r = n_hub + blockIdx.x * kWideWarps + wid;             // the first two rows of a warp are fixed
+    int r_next = r + total_warps;
+    unsigned raw_nn = 0;                                       // row after next: lane 0's pending request
+    if (counter && lane == 0) raw_nn = atomicAdd(counter, 1u);
     int row = 0, start = 0, end = 0, pre_c = 0;
     float pre_w = 0.f;
     float own[4] = {0.f, 0.f, 0.f, 0.f};
@@ -388,7 +400,13 @@ cheb_wide_kernel(const __grid_constant__ WideParams p) {
         load_own(row, own);
     }
     while (r < n_rows) {
-        const int r_next = r + total_warps;
+        // the row after next: static stride without a counter, else what the counter handed out
+        // one row ago (a new request goes out now)
+        int r_nn = r_next + total_warps;
+        if (counter) {
+            r_nn = n_hub + 2 * total_warps + (int)__shfl_sync(0xffffffffu, raw_nn, 0);
+            if (lane == 0) raw_nn = atomicAdd(counter, 1u);
+        }
         int row_n = 0, start_n = 0, end_n = 0;
         if (r_next < n_rows) {
             row_n = p.perm ? __ldg(p.perm + r_next) : r_next;
@@ -414,7 +432,7 @@ cheb_wide_kernel(const __grid_constant__ WideParams p) {
             for (int v = 0; v < 4; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], o);
         }
         wide_epilogue<ALIGNED, PEER>(p, row, grow, FL, fcol, ncol, writer, acc, pol_stream, have_own, own);
-        r = r_next; row = row_n; start = start_n; end = end_n; pre_c = pre_c_n; pre_w = pre_w_n;
+        r = r_next; r_next = r_nn; row = row_n; start = start_n; end = end_n; pre_c = pre_c_n; pre_w = pre_w_n;
 #pragma unroll
         for (int v = 0; v < 4; ++v) own[v] = own_n[v];
     }
