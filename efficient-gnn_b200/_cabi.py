@@ -12,7 +12,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libegnn_b200.so")
+LIB_PATH = os.environ.get("EGNN_LIB_PATH") or os.path.join(_HERE, "lib", "libegnn_b200.so")   # override: tuning builds
 ABI_VERSION = 4
 
 # every symbol include/egnn_b200.h declares: name -> (restype, argtypes)

@@ -110,18 +110,25 @@ static RingConfig ring_config(int ldy) {
     return c;
 }
 
-template <int NZ_LOG2, bool PEER>
-static int launch_wide_np(const WideParams& p, dim3 grid, cudaStream_t st) {
+template <int NZ_LOG2, bool PEER, bool DYN>
+static int launch_wide_npd(const WideParams& p, dim3 grid, cudaStream_t st) {
     const bool aligned = (p.F % 4) == 0;
     if (p.vals) {
-        if (aligned) cheb_wide_kernel<NZ_LOG2, true, true, PEER><<<grid, kWideBlock, 0, st>>>(p);
-        else cheb_wide_kernel<NZ_LOG2, true, false, PEER><<<grid, kWideBlock, 0, st>>>(p);
+        if (aligned) cheb_wide_kernel<NZ_LOG2, true, true, PEER, DYN><<<grid, kWideBlock, 0, st>>>(p);
+        else cheb_wide_kernel<NZ_LOG2, true, false, PEER, DYN><<<grid, kWideBlock, 0, st>>>(p);
     } else {
-        if (aligned) cheb_wide_kernel<NZ_LOG2, false, true, PEER><<<grid, kWideBlock, 0, st>>>(p);
-        else cheb_wide_kernel<NZ_LOG2, false, false, PEER><<<grid, kWideBlock, 0, st>>>(p);
+        if (aligned) cheb_wide_kernel<NZ_LOG2, false, true, PEER, DYN><<<grid, kWideBlock, 0, st>>>(p);
+        else cheb_wide_kernel<NZ_LOG2, false, false, PEER, DYN><<<grid, kWideBlock, 0, st>>>(p);
     }
     EGNN_LAUNCH_CHECK("cheb_wide_kernel launch");
     return EGNN_OK;
+}
+
+// DYN instantiation (single GPU only): rows handed out from p.row_counter
+template <int NZ_LOG2, bool PEER>
+static int launch_wide_np(const WideParams& p, dim3 grid, cudaStream_t st) {
+    if (!PEER && p.row_counter) return launch_wide_npd<NZ_LOG2, false, true>(p, grid, st);
+    return launch_wide_npd<NZ_LOG2, PEER, false>(p, grid, st);
 }
 
 // PEER instantiation: operand in the exchange window, written by the other GPUs (world > 1)

@@ -301,7 +301,7 @@ __device__ __forceinline__ void wide_accumulate(const WideParams& p, int qs, int
     for (int v = 0; v < 4; ++v) sum[v] = hi[v] + acc[v];
 }
 
-template <int NZ_LOG2, bool HAS_VALS, bool ALIGNED, bool PEER>
+template <int NZ_LOG2, bool HAS_VALS, bool ALIGNED, bool PEER, bool DYN>
 __global__ void __launch_bounds__(kWideBlock, kWideMinBlocks)
 cheb_wide_kernel(const __grid_constant__ WideParams p) {
     __shared__ float hub_part[kWideWarps][128];
@@ -363,18 +363,19 @@ cheb_wide_kernel(const __grid_constant__ WideParams p) {
     }
 
     // ---- phase B: one row per warp ---------------------------------------------------
-    // Rows are taken longest first.  Handing them out from a counter (greedy longest-processing-
-    // time schedule) matters on short-row graphs: dealt out cyclically, warp 0 gets the longest
-    // row of every round - on the arxiv shape (15 entries per row on average, 660 at most, 36
-    // rounds) the first warps carry twice the work of the last (ncu: slowest SM active 516 k
-    // cycles, average 364 k).  The row after next is requested while this one is summed, so the
-    // atomic's latency and the next row's pointer loads stay off the critical path.
+    // Rows are taken longest first.  DYN: handed out from a counter (greedy longest-processing-
+    // time schedule), which matters on short-row graphs: dealt out cyclically, warp 0 gets the
+    // longest row of every round - on the arxiv shape (15 entries per row on average, 660 at
+    // most, 36 rounds) the first warps carry twice the work of the last (ncu: slowest SM active
+    // 516 k cycles, average 364 k).  The row after next is requested while this one is summed,
+    // so the atomic's latency and the next row's pointer loads stay off the critical path.
+    // A separate instantiation: the bookkeeping costs the long-row shapes 15-20 % when compiled in.
     const int total_warps = gridDim.x * kWideWarps;
-    unsigned* counter = p.row_counter ? p.row_counter + blockIdx.y : nullptr;
+    unsigned* counter = DYN ? p.row_counter + blockIdx.y : nullptr;
     int r = n_hub + blockIdx.x * kWideWarps + wid;             // the first two rows of a warp are fixed
     int r_next = r + total_warps;
     unsigned raw_nn = 0;                                       // row after next: lane 0's pending request
-    if (counter && lane == 0) raw_nn = atomicAdd(counter, 1u);
+    if (DYN && lane == 0) raw_nn = atomicAdd(counter, 1u);
     int row = 0, start = 0, end = 0, pre_c = 0;
     float pre_w = 0.f;
     float own[4] = {0.f, 0.f, 0.f, 0.f};
@@ -403,7 +404,7 @@ cheb_wide_kernel(const __grid_constant__ WideParams p) {
         // the row after next: static stride without a counter, else what the counter handed out
         // one row ago (a new request goes out now)
         int r_nn = r_next + total_warps;
-        if (counter) {
+        if (DYN) {
             r_nn = n_hub + 2 * total_warps + (int)__shfl_sync(0xffffffffu, raw_nn, 0);
             if (lane == 0) raw_nn = atomicAdd(counter, 1u);
         }
