@@ -18,6 +18,9 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
+SURVEY_FLOOR_WORST = {}      # tag -> worst element-wise ratio at SURVEY 8c's original 1e-3 floor (printed, not enforced)
+
+
 def check_parts(res, ref_T, ref_S, ref_H, tag=""):
     worst = []
     for i, (got, ref) in enumerate(zip(res.orders, ref_T)):
@@ -27,6 +30,11 @@ def check_parts(res, ref_T, ref_S, ref_H, tag=""):
         assert err <= TOL, f"{tag} order {i}: rel max err {err:.3e}"
         ratio = elementwise_ratio(g, ref, TOL)
         assert ratio <= 1.0, f"{tag} order {i}: element-wise bound exceeded x{ratio:.2f}"
+        at_survey_floor = elementwise_ratio(g, ref, TOL, floor=1e-3)
+        SURVEY_FLOOR_WORST[tag] = max(SURVEY_FLOOR_WORST.get(tag, 0.0), at_survey_floor)
+    if tag:
+        print(f"\n[{tag}] worst element-wise ratio at the enforced 5e-2 floor <= 1; at SURVEY's 1e-3 floor: "
+              f"x{SURVEY_FLOOR_WORST[tag]:.2f}; norm-wise worst {max(worst):.2e}")
     for j, rs in enumerate(ref_S):
         g = res.combined[:, j, :].cpu().numpy()
         assert rel_max_err(g, rs) <= TOL, f"{tag} S[{j}]"
