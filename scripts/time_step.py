@@ -21,7 +21,7 @@ acc = []
 for _ in range(20):
     egnn.graph_wavelet_features(g, k=k, _use_sell=True)
     torch.cuda.synchronize()
-    acc.append(read_phase_stamps(plan, k))
+    acc.append(read_phase_stamps(plan, k, first_operand_in_kernel=False))
 # per-CTA trace of one launch: [stage done, slices done, rows done] per order
 enable_phase_stamps(plan, True, trace=True)
 egnn.graph_wavelet_features(g, k=k, _use_sell=True)
@@ -31,8 +31,8 @@ glob, per = st[:64], st[64:].reshape(plan.n_cta, 64)
 blk = info[:plan.n_cta]
 # global stamps: [0] start, [1] after prologue barrier, then per order: after barrier 1, after barrier 2 (or end)
 for order in range(1, k + 1):
-    rel0 = glob[1 + 2 * (order - 1)]                 # release of the barrier that opened this order
-    rel1 = glob[2 + 2 * (order - 1)]                 # release of barrier 1
+    rel0 = glob[0 + 2 * (order - 1)]                 # start of the order on CTA 0 (kernel start / its own rows of the previous order done)
+    rel1 = glob[1 + 2 * (order - 1)]                 # release of barrier 1
     stage, done, rows = per[:, 3 * (order - 1)], per[:, 3 * (order - 1) + 1], per[:, 3 * (order - 1) + 2]
     f = lambda x: f"min {x.min() / 1e3:.1f} mean {x.mean() / 1e3:.1f} max {x.max() / 1e3:.1f}"
     print(f"order {order}: stage done after open: {f(stage - rel0)}; slices done after open: {f(done - rel0)}; "
