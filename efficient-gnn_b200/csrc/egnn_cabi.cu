@@ -13,6 +13,7 @@
 #include "sell.cuh"
 #include "sell_step.cuh"
 #include "surrogate.cuh"
+#include "blocked.cuh"
 #include "wide.cuh"
 
 namespace egnn {
@@ -28,6 +29,7 @@ void set_error(const char* fmt, ...) {
 
 static int device_sm_count();
 constexpr int kWideMinF = 8;             // narrower signals keep the multi-row-per-warp kernel (cheb.cuh)
+constexpr int64_t kBlockedMinNnz = int64_t(1) << 22;   // below this the CSR is L2-resident: the generic kernel is as fast
 constexpr int kWideDynamicMaxDegree = 64;   // mean entries per row below which the wide kernel hands rows out dynamically
 
 static int pow2_ceil_log2(int64_t x) {
@@ -499,6 +501,23 @@ int egnn_row_order(const int32_t* rowptr, int64_t n, int32_t* order_out, void* w
     return EGNN_OK;
 }
 
+// Column blocks of the shared-memory staged narrow paths (SELL plan and plan-free blocked kernel)
+static void narrow_geometry(int64_t n, int* n_blocks, int* col_block) {
+    const int64_t cb_max = 49152;                     // 192 KB of float32 operand per CTA
+    const int64_t c = ceil_div64(n, cb_max);
+    int64_t cb = ceil_div64(ceil_div64(n, c), 32) * 32;
+    if (cb > 65504) cb = 65504;
+    *n_blocks = (int)ceil_div64(n, cb);
+    *col_block = (int)cb;
+}
+
+static size_t blocked_ws_bytes(int64_t n) {
+    int C = 1, CB = 32;
+    narrow_geometry(n > 0 ? n : 1, &C, &CB);
+    return align_up(4 * (size_t)(C + 1) * (size_t)n, 256) + align_up(4 * (size_t)C * (size_t)n, 256) +
+           align_up(4 * (size_t)EGNN_MAX_ORDER * (size_t)C, 256);
+}
+
 size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f) {
     // two T ping-pong slabs + two pre-scaled gather slabs (narrow F only)
     // f <= 4: two T slabs + two pre-scaled slabs; 4 < f < 8: two T slabs; f >= 8: two pre-scaled slabs
@@ -506,7 +525,8 @@ size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f) {
     const size_t slab = align_up(sizeof(float) * (size_t)n * width, 256);
     // wide path: + one row counter per (order, feature tile) for the dynamic row schedule
     const size_t counters = f >= kWideMinF ? align_up(sizeof(unsigned) * (size_t)EGNN_MAX_ORDER * (size_t)((width + 127) / 128), 256) : 0;
-    return slab * (f <= 4 ? 4 : 2) + counters + 256;
+    // f == 1: + segment table, partial sums and counters of the plan-free blocked kernel
+    return slab * (f <= 4 ? 4 : 2) + counters + (f == 1 ? blocked_ws_bytes(n) : 0) + 256;
 }
 
 int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float* vals_or_null,
@@ -517,7 +537,7 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
                       const float* delta_val_host, int32_t n_delta, void* workspace,
                       size_t workspace_bytes, egnn_stream_t stream, void* const* order_events_host,
                       const egnn_sell_plan* sell_plan, const int32_t* row_order_or_null,
-                      const float* y0_or_null) {
+                      const float* y0_or_null, int32_t rows_sorted) {
     EGNN_REQUIRE(rowptr && dinv && iso && x0 && out && coeffs_host, "null pointer");
     EGNN_REQUIRE(nnz == 0 || colidx, "null colidx");
     EGNN_REQUIRE(n >= 0 && n < (int64_t(1) << 31) && nnz >= 0 && nnz < (int64_t(1) << 31), "n/nnz out of int32 range");
@@ -597,6 +617,69 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
                 rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[e], st), "event record");
                 if (rc) return rc;
             }
+        }
+        return EGNN_OK;
+    }
+
+    if (f == 1 && rows_sorted && (nnz >= kBlockedMinNnz || rows_sorted == 2) && nnz > 0) {
+        // first use of a large graph (no SELL plan yet): plan-free column-blocked kernel (blocked.cuh)
+        int C = 1, CB = 32;
+        narrow_geometry(n, &C, &CB);
+        char* extra = ws + 4 * slab;
+        int32_t* seg = (int32_t*)extra;
+        float* part = (float*)(extra + align_up(4 * (size_t)(C + 1) * (size_t)n, 256));
+        unsigned* counters = (unsigned*)((char*)part + align_up(4 * (size_t)C * (size_t)n, 256));
+        rc = check_cuda(cudaMemsetAsync(counters, 0, sizeof(unsigned) * (size_t)k * (size_t)C, st), "memset batch counters");
+        if (rc) return rc;
+        blocked_bounds_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(rowptr, colidx, (int)n, C, CB, seg);
+        EGNN_LAUNCH_CHECK("blocked_bounds_kernel launch");
+        const size_t smem = sizeof(float) * (size_t)CB;
+        const void* fn = vals_or_null ? (const void*)blocked_spmv_kernel<true> : (const void*)blocked_spmv_kernel<false>;
+        rc = check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        "cudaFuncSetAttribute(blocked_spmv_kernel)");
+        if (rc) return rc;
+        BlockedParams bp{};
+        bp.colidx = colidx; bp.vals = vals_or_null; bp.seg = seg; bp.part = part;
+        bp.n = (int32_t)n; bp.C = C; bp.CB = CB; bp.n_cta = device_sm_count();
+        if (bp.n_cta < C) bp.n_cta = C;
+        BlockedEpilogueParams ep{};
+        ep.delta = p.delta;
+        ep.part = part; ep.dinv = dinv; ep.iso = iso; ep.out = out; ep.n = (int32_t)n; ep.C = C; ep.S = n_scales;
+        ep.a = op_scale; ep.b = op_shift;
+        const float* t_prev = x0;
+        const float* t_prev2 = nullptr;
+        for (int order = 1; order <= k; ++order) {
+            const bool last = order == k;
+            float* t_out;
+            if (t_all_or_null) t_out = t_all_or_null + (size_t)order * slab_elems;
+            else if (last) t_out = nullptr;
+            else if (order == 1) t_out = tbuf[0];
+            else if (order == 2) t_out = tbuf[1];
+            else t_out = const_cast<float*>(t_prev2);
+            if (order_events_host) {
+                rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1)], st), "event record");
+                if (rc) return rc;
+            }
+            bp.y = ybuf[(order - 1) & 1];
+            bp.counter = counters + (size_t)(order - 1) * C;
+            if (vals_or_null) blocked_spmv_kernel<true><<<bp.n_cta, kBlockedThreads, smem, st>>>(bp);
+            else blocked_spmv_kernel<false><<<bp.n_cta, kBlockedThreads, smem, st>>>(bp);
+            EGNN_LAUNCH_CHECK("blocked_spmv_kernel launch");
+            ep.y_prev = bp.y; ep.tprev = t_prev; ep.tprev2 = t_prev2; ep.tk = t_out;
+            ep.y_out = last ? nullptr : ybuf[order & 1];
+            ep.first = order == 1; ep.normalize = last && normalize_l1;
+            for (int s = 0; s < n_scales; ++s) {
+                ep.c_prev[s] = coeffs_host[s * (k + 1) + order - 1];
+                ep.c_k[s] = coeffs_host[s * (k + 1) + order];
+            }
+            blocked_epilogue_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(ep);
+            EGNN_LAUNCH_CHECK("blocked_epilogue_kernel launch");
+            if (order_events_host) {
+                rc = check_cuda(cudaEventRecord((cudaEvent_t)order_events_host[2 * (order - 1) + 1], st), "event record");
+                if (rc) return rc;
+            }
+            t_prev2 = t_prev;
+            t_prev = t_out;
         }
         return EGNN_OK;
     }
@@ -773,12 +856,10 @@ int egnn_cheb_order_sharded(const int32_t* rowptr_local, const int32_t* colidx_l
 int egnn_sell_geometry(int64_t n, int64_t nnz, int32_t* n_blocks, int32_t* col_block, int32_t* lmax) {
     EGNN_REQUIRE(n_blocks && col_block && lmax, "null pointer");
     EGNN_REQUIRE(n >= 1, "bad shape");
-    const int64_t cb_max = 49152;                     // 192 KB of float32 operand per CTA
-    int64_t c = ceil_div64(n, cb_max);
-    int64_t cb = ceil_div64(ceil_div64(n, c), 32) * 32;
-    if (cb > 65504) cb = 65504;
-    *n_blocks = (int32_t)ceil_div64(n, cb);
-    *col_block = (int32_t)cb;
+    int nb = 1, cb = 32;
+    narrow_geometry(n, &nb, &cb);
+    *n_blocks = nb;
+    *col_block = cb;
     *lmax = 256;
     (void)nnz;
     return EGNN_OK;

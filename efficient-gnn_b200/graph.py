@@ -195,6 +195,7 @@ class CsrGraph:
         self._sell_structural = False   # the False above is final (weighted / unsorted / empty), not a threshold
         self.narrow_calls = 0      # F = 1 passes run on this graph (the plan is built on the second)
         self._row_order = None     # lazily built processing order of the wide kernel
+        self._sorted = None        # lazily read result of the degree pass's sortedness check
         self._y0 = None            # lazily built dinv * x0 (first operand of the narrow path, default signal)
 
     def _release_scratch(self):
@@ -209,6 +210,13 @@ class CsrGraph:
                                             _cabi.ptr(self._colsum), _cabi.ptr(self._unsorted_flag), _stream()),
                         "egnn_graph_prep")
         self._release_scratch()
+
+    def rows_sorted(self) -> bool:
+        """Every CSR row is sorted by column (checked by the degree pass; one
+        4-byte D2H read on first use)."""
+        if self._sorted is None:
+            self._sorted = not bool(self._unsorted_flag.item())
+        return self._sorted
 
     def y0(self):
         """``dinv * x0`` of the default signal: the first gather operand of the
@@ -257,7 +265,7 @@ class CsrGraph:
         self._sell_structural = True
         if self.vals is not None or self.n < 1 or self.nnz == 0:
             return None
-        if bool(self._unsorted_flag.item()):
+        if not self.rows_sorted():
             return None
         self._sell_structural = False
         lib = _cabi.load()

@@ -25,7 +25,7 @@ import torch.nn.functional as F
 from . import _cabi
 from .graph import CsrGraph, as_graph
 
-__all__ = ["LaplacianOperator", "compute_normalized_laplacian", "chebyshev_polynomials",
+__all__ = ["LaplacianOperator", "ExplicitOperator", "compute_normalized_laplacian", "chebyshev_polynomials",
            "graph_wavelet_features", "heat_coefficients", "WaveletResult", "WaveletSession", "WATS", "accuracy"]
 
 
@@ -73,13 +73,18 @@ def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_
     dinv, iso = (graph.dinv, graph.iso) if degree_vectors is None else degree_vectors
     d_rows, d_cols, d_vals = ([], [], []) if deltas is None else deltas
     plan = None
-    if f == 1 and k >= 1 and use_sell is not False:
+    blocked = 0                   # plan-free column-blocked kernel (csrc/blocked.cuh): first use of a large graph
+    if use_sell == "blocked":     # tests: force it whatever the size
+        blocked = 2 if (f == 1 and graph.rows_sorted()) else 0
+    elif f == 1 and k >= 1 and use_sell is not False:
         # The SELL re-layout costs about as much as 25 generic-kernel orders on the Reddit shape, so it is
         # built when a graph is used for the second time (calibrator construction computes the features
         # once; the UGCA recompute loop and benchmarks call again and again on the same graph).
         graph.narrow_calls += 1
         if use_sell or graph.narrow_calls >= 2 or graph.has_sell_plan():
             plan = graph.sell_plan(force=bool(use_sell))
+        if plan is None and graph.rows_sorted():
+            blocked = 1
     row_order = graph.row_order() if (f >= WIDE_MIN_F and k >= 1) else None
     with torch.cuda.device(dev):
         out = torch.empty((n, n_scales, f), dtype=torch.float32, device=dev)
@@ -97,7 +102,8 @@ def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_
             _cabi.host_array(C.c_float, [float(v) for v in d_vals]), len(d_rows),
             _cabi.ptr(ws), ws_bytes, _stream(), order_events,
             None if plan is None else C.byref(plan), _cabi.ptr(row_order),
-            _cabi.ptr(graph.y0()) if (plan is not None and default_signal) else None), "egnn_cheb_wavelet")
+            _cabi.ptr(graph.y0()) if (plan is not None and default_signal) else None,
+            blocked), "egnn_cheb_wavelet")
     return out, t_all
 
 
@@ -166,13 +172,68 @@ def compute_normalized_laplacian(adj) -> LaplacianOperator:
     return LaplacianOperator(as_graph(adj))
 
 
+class ExplicitOperator:
+    """An explicit sparse matrix (what the reference hands to ``chebyshev_polynomials``: the scipy
+    ``L_rescaled`` of calibration/WATS.py:55) as a device operator.  The off-diagonal entries go
+    through the same fused kernels as a weighted CSR (unit normaliser, no implicit diagonal), the
+    stored diagonal is applied as a per-row scale; entries are rounded to float32."""
+
+    def __init__(self, mat):
+        import scipy.sparse as sp
+        m = sp.csr_matrix(mat, copy=True)
+        if m.shape[0] != m.shape[1]:
+            raise ValueError("operator must be square")
+        m.sum_duplicates()
+        m.sort_indices()
+        n = m.shape[0]
+        diag = np.asarray(m.diagonal(), dtype=np.float32)
+        off = (m - sp.diags(m.diagonal(), format="csr")).tocsr()
+        off.eliminate_zeros()
+        off.sort_indices()
+        _cabi.require_device()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.graph = CsrGraph(torch.from_numpy(off.indptr.astype(np.int32)).to(dev),
+                              torch.from_numpy(off.indices.astype(np.int32)).to(dev),
+                              torch.from_numpy(off.data.astype(np.float32)).to(dev), n)
+        self.diag = torch.from_numpy(diag).to(dev)
+        self.unit = (torch.ones(n, dtype=torch.float32, device=dev), torch.ones(n, dtype=torch.uint8, device=dev))
+        self.shape = (n, n)
+
+    def __matmul__(self, x):
+        xt = torch.as_tensor(x)
+        vec = xt.dim() == 1
+        xt = (xt.unsqueeze(1) if vec else xt).to(device=self.diag.device, dtype=torch.float32)
+        # kernel: theta * x - a * dinv_i * sum_{j != i} v_ij dinv_j x_j with a = -1, dinv = 1, theta = 0
+        out, _ = _run_cheb(self.graph, xt, 1, np.array([[0.0, 1.0]]), -1.0, 0.0, False, False,
+                           degree_vectors=self.unit, use_sell=False)
+        y = out[:, 0, :] + self.diag.unsqueeze(1) * xt
+        return y[:, 0] if vec else y
+
+
 def chebyshev_polynomials(L, k, X0):
     """``[T_0 .. T_k]`` with ``T_1 = L X0``, ``T_i = 2 L T_{i-1} - T_{i-2}``
-    (calibration/WATS.py:29-37).  ``L`` is a :class:`LaplacianOperator`
-    (normally the rescaled one); returns k+1 float32 device tensors ``[N,F]``."""
-    if not isinstance(L, LaplacianOperator):
-        raise TypeError("L must come from compute_normalized_laplacian (LaplacianOperator)")
+    (calibration/WATS.py:29-37).  ``L`` is a :class:`LaplacianOperator` (what
+    ``compute_normalized_laplacian`` returns, normally rescaled: all orders in the
+    fused kernels) or an explicit scipy sparse matrix as in the reference (one
+    kernel application per order); returns k+1 float32 device tensors ``[N,F]``."""
     k = int(k)
+    if not isinstance(L, LaplacianOperator):
+        try:
+            import scipy.sparse as sp
+            explicit = sp.issparse(L)
+        except ImportError:       # pragma: no cover
+            explicit = False
+        if not explicit:
+            raise TypeError("L must be a LaplacianOperator (compute_normalized_laplacian) or a scipy sparse matrix")
+        op = ExplicitOperator(L)
+        x0 = torch.as_tensor(X0)
+        x0 = (x0.unsqueeze(1) if x0.dim() == 1 else x0).to(device=op.diag.device, dtype=torch.float32)
+        t_k = [x0]
+        if k > 0:
+            t_k.append(op @ x0)
+        for _ in range(2, k + 1):
+            t_k.append(2 * (op @ t_k[-1]) - t_k[-2])
+        return t_k
     coeffs = np.zeros((1, k + 1))
     _, t_all = _run_cheb(L.graph, torch.as_tensor(X0), k, coeffs, L.scale, L.shift, False, True)
     return [t_all[i] for i in range(k + 1)]

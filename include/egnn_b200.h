@@ -195,7 +195,12 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
  * f >= 8: longest rows first, hub rows summed by a whole CTA); NULL = CSR order.
  * y0_or_null (SELL plan only): dinv (.) x0 [n] when the caller already holds it
  * (fixed per graph for the default signal log1p(degree)): the step kernel then
- * skips computing it.  Must match dinv and x0 (so not with edge flips).        */
+ * skips computing it.  Must match dinv and x0 (so not with edge flips).
+ * rows_sorted: non-zero when every CSR row is sorted by column (the unsorted
+ * flag of egnn_graph_prep): f == 1 without a plan on a large graph (nnz >= 4 M)
+ * then runs the plan-free column-blocked kernel (csrc/blocked.cuh: operand
+ * staged in shared memory, no re-layout) instead of the generic CSR kernel
+ * (2: also on small graphs - tests).                                          */
 size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f);
 int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx,
                       const float* vals_or_null, const float* dinv,
@@ -208,7 +213,7 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx,
                       void* workspace, size_t workspace_bytes,
                       egnn_stream_t stream, void* const* order_events_host,
                       const egnn_sell_plan* sell_plan_or_null, const int32_t* row_order_or_null,
-                      const float* y0_or_null);
+                      const float* y0_or_null, int32_t rows_sorted);
 
 /* Processing order of the wide-signal kernel (new in this build): rows by
  * descending stored-entry count.  order_out: int32[n + 1] - the permutation,

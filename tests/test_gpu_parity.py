@@ -382,3 +382,24 @@ def test_errors_are_exceptions():
         egnn.graph_wavelet_features(g, deltas=([9], [0], [1.0]))             # index out of range
     with pytest.raises(TypeError):
         egnn.chebyshev_polynomials(c["lt"], 3, c["X0"])
+
+
+@pytest.mark.parametrize("name", ["kat_path", "cora_noloop", "cora_loops", "directed_weighted", "cora_wide8"])
+def test_chebyshev_polynomials_on_the_reference_scipy_operator(name):
+    """The reference calls chebyshev_polynomials(L_rescaled, k, X0) with an explicit scipy matrix
+    (calibration/WATS.py:55,62): the drop-in accepts that too (isolated nodes carry -1 on the
+    stored diagonal, every other diagonal entry is absent)."""
+    c = load_case(name)
+    got = egnn.chebyshev_polynomials(c["lt"], c["k"], c["X0"])
+    assert len(got) == c["k"] + 1
+    for i, (g, ref) in enumerate(zip(got, c["T"])):
+        assert rel_max_err(g.cpu().numpy(), ref) <= TOL, f"{name} order {i}"
+    # and a general matrix with an arbitrary diagonal, against scipy
+    rng = np.random.default_rng(7)
+    m = sp.random(300, 300, density=0.03, random_state=3, format="csr", dtype=np.float64)
+    m = m + sp.diags(rng.uniform(-1, 1, 300))
+    x = rng.standard_normal((300, 3)).astype(np.float32)
+    ref = [x.astype(np.float64), m @ x]
+    ref.append(2 * m @ ref[-1] - ref[-2])
+    for g, r in zip(egnn.chebyshev_polynomials(m, 2, x), ref):
+        assert rel_max_err(g.cpu().numpy(), r) <= TOL

@@ -164,3 +164,82 @@ def test_reddit_shape_uses_the_plan_from_the_second_pass():
     plan = g.sell_plan()
     print(f"\npadding: entries {plan.n_entries} / nnz {g.nnz} = {plan.n_entries / g.nnz:.4f}; "
           f"vrows {plan.n_vrows}, blocks {plan.n_blocks} x {plan.col_block}")
+
+
+# ---- the plan-free column-blocked kernel (csrc/blocked.cuh): first use of a large graph ----------
+@pytest.mark.parametrize("name", ["kat_path", "kat_path_loops", "cora_noloop", "cora_loops", "pubmed_noloop",
+                                  "cora_k0", "cora_k1", "cora_k6_s04", "directed_weighted"])
+def test_golden_cases_through_the_blocked_kernel(name):
+    c = load_case(name)
+    if c["custom_x0"]:
+        pytest.skip("one-column default signal only")
+    res = egnn.graph_wavelet_features(c["adj"], k=c["k"], s=c["s"], return_parts=True, _use_sell="blocked")
+    check_parts(res, c["T"], [c["S"]], [c["H"]], name + " blocked")
+    fused = egnn.graph_wavelet_features(c["adj"], k=c["k"], s=c["s"], _use_sell="blocked")
+    sure = np.abs(c["S"]) > 1e-4 * np.abs(c["S"]).max()
+    np.testing.assert_allclose(fused.cpu().numpy()[sure], c["H"].astype(np.float32)[sure], rtol=0, atol=1e-6)
+
+
+def test_blocked_kernel_hub_rows_flips_and_determinism():
+    n = 70_001                                # two column blocks, a hub row of 70,000 entries
+    hub = np.zeros(n - 1, dtype=np.int64)
+    leaves = np.arange(1, n, dtype=np.int64)
+    adj = sp.csr_matrix((np.ones(2 * (n - 1), np.float32), (np.concatenate([hub, leaves]), np.concatenate([leaves, hub]))),
+                        shape=(n, n))
+    x0 = np.random.default_rng(0).uniform(0.5, 1.5, (n, 1)).astype(np.float32)
+    g = egnn.CsrGraph.from_scipy(adj)
+    res = egnn.graph_wavelet_features(g, k=3, X0=torch.from_numpy(x0), return_parts=True, _use_sell="blocked")
+    p = orc.wavelet_parts(adj, k=3, x0=x0)
+    check_parts(res, p["T"], p["S"], p["H"], "star blocked")
+    again = egnn.graph_wavelet_features(g, k=3, X0=torch.from_numpy(x0), return_parts=True, _use_sell="blocked")
+    for a, b in zip(res.orders, again.orders):
+        assert torch.equal(a, b)
+    # edge flips on top of the CSR
+    c = load_case("cora_loops")
+    dense = c["adj"].toarray()
+    target, others = 17, [3, 500, 1200, 2000, 2700]
+    rows, cols, vals = [], [], []
+    pert = dense.copy()
+    for j in others:
+        v = -2 * dense[target, j] + 1
+        pert[target, j] += v
+        pert[j, target] += v
+        rows += [target, j]; cols += [j, target]; vals += [float(v), float(v)]
+    gc = egnn.CsrGraph.from_scipy(c["adj"])
+    res = egnn.graph_wavelet_features(gc, deltas=(rows, cols, vals), return_parts=True, _use_sell="blocked")
+    pp = orc.wavelet_parts(sp.csr_matrix(pert.astype(np.float32)))
+    check_parts(res, pp["T"], pp["S"], pp["H"], "delta blocked")
+
+
+def test_first_call_on_a_large_graph_runs_the_blocked_kernel():
+    """nnz >= 4 M, sorted rows, no plan yet: the default first call takes the blocked kernel and agrees
+    with the generic CSR kernel and with the SELL plan of the second call."""
+    rp, ci, n = synth.synth_csr("reddit", self_loops=True, device="cuda", scale=0.25)
+    g = egnn.CsrGraph(rp, ci, None, n)
+    assert g.nnz >= (1 << 22) and g.rows_sorted()
+    first = egnn.graph_wavelet_features(g, k=3, s=[0.8, 1.6], return_parts=True)        # blocked
+    generic = egnn.graph_wavelet_features(g, k=3, s=[0.8, 1.6], return_parts=True, _use_sell=False)
+    second = egnn.graph_wavelet_features(g, k=3, s=[0.8, 1.6], return_parts=True)       # SELL plan
+    assert g.has_sell_plan()
+    for ta, tb, tc in zip(first.orders, generic.orders, second.orders):
+        assert ((ta - tb).abs().max() / tb.abs().max()).item() <= 2e-6
+        assert ((tc - tb).abs().max() / tb.abs().max()).item() <= 2e-6
+
+
+def test_force_rebuilds_a_plan_the_thresholds_rejected_and_inputs_are_not_mutated():
+    """A non-forced call that rejects a small graph must not pin `no plan` for a later forced call
+    (only structural disqualifiers are final); from_scipy must not canonicalise the caller's CSR."""
+    c = load_case("cora_loops")
+    g = egnn.CsrGraph.from_scipy(c["adj"])
+    assert g.sell_plan() is None                       # too small for the thresholds
+    assert g.sell_plan(force=True) is not None         # but a forced build still works
+    w = load_case("directed_weighted")
+    gw = egnn.CsrGraph.from_scipy(w["adj"])
+    assert gw.sell_plan() is None and gw.sell_plan(force=True) is None      # weighted: final
+    # unsorted, duplicate-carrying caller matrix stays as the caller built it
+    unsorted = sp.csr_matrix((np.ones(4, np.float32), np.array([2, 0, 1, 0], np.int32), np.array([0, 2, 3, 4], np.int32)),
+                             shape=(3, 3))
+    before = (unsorted.indices.copy(), unsorted.indptr.copy(), unsorted.data.copy(), unsorted.has_sorted_indices)
+    egnn.CsrGraph.from_scipy(unsorted)
+    assert np.array_equal(unsorted.indices, before[0]) and np.array_equal(unsorted.indptr, before[1])
+    assert np.array_equal(unsorted.data, before[2])
