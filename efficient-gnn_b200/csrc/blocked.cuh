@@ -115,30 +115,57 @@ blocked_spmv_kernel(const __grid_constant__ BlockedParams p) {
         }
         const int row_base = batch * kBlockedBatch;
         float mine = 0.f;                                      // lane l keeps the sum of row row_base + l
+        // the first four index loads of the NEXT row are in flight while this row is summed
+        int cj[4];
+        float wj[4];
+        auto load4 = [&](int e, int hi, int row, int (&cc)[4], float (&ww)[4]) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = e + 32 * u;
+                cc[u] = q < hi ? ld_stream_i32(p.colidx + q) : row;
+                ww[u] = (HAS_VALS && q < hi) ? ld_stream_f32(p.vals + q) : 1.f;
+            }
+        };
+        {
+            const int lo0 = __shfl_sync(0xffffffffu, my_lo, 0), hi0 = __shfl_sync(0xffffffffu, my_hi, 0);
+            load4(lo0 + lane, hi0, row_base, cj, wj);
+        }
         for (int r = 0; r < kBlockedBatch; ++r) {
             const int lo = __shfl_sync(0xffffffffu, my_lo, r);
             const int hi = __shfl_sync(0xffffffffu, my_hi, r);
-            if (lo >= hi) continue;                            // warp-uniform
             const int row = row_base + r;
+            int cn[4];
+            float wn[4];
+            if (r + 1 < kBlockedBatch) {
+                const int lo_n = __shfl_sync(0xffffffffu, my_lo, r + 1), hi_n = __shfl_sync(0xffffffffu, my_hi, r + 1);
+                load4(lo_n + lane, hi_n, row + 1, cn, wn);
+            }
+            // two-level sum (the oracle accumulates in float64): float32 over 64 entries per lane,
+            // those chunks and the 32 lanes in float64, always in the same order
             float acc = 0.f;
-            for (int e = lo + lane; e < hi; e += 128) {        // four coalesced index loads in flight
-                int cj[4];
-                float wj[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int q = e + 32 * u;
-                    cj[u] = q < hi ? ld_stream_i32(p.colidx + q) : row;
-                    wj[u] = (HAS_VALS && q < hi) ? ld_stream_f32(p.vals + q) : 1.f;
-                }
+            double accd = 0.0;
+            int since = 0;
+            for (int e = lo + lane; e < hi; e += 128) {        // four coalesced index loads per trip
+                if (e != lo + lane) load4(e, hi, row, cj, wj);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float w = cj[u] == row ? 0.f : wj[u];           // stored self loops are not part of L; padding lanes too
                     const int loc = cj[u] == row ? 0 : cj[u] - col0;
                     acc = fmaf(w, ysm[loc], acc);
                 }
+                if (++since == 16) { accd += (double)acc; acc = 0.f; since = 0; }
             }
-            acc = warp_sum(acc);
-            if (lane == r) mine = acc;
+            accd += (double)acc;
+            if (hi - lo > 2048) {                              // long segment: lanes combined in float64
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) accd += __shfl_xor_sync(0xffffffffu, accd, o);
+                if (lane == r) mine = (float)accd;
+            } else {
+                const float a = warp_sum((float)accd);
+                if (lane == r) mine = a;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { cj[u] = cn[u]; wj[u] = wn[u]; }
         }
         const int row = row_base + lane;
         if (row < p.n) p.part[(size_t)c * p.n + row] = mine;

@@ -381,7 +381,7 @@ def test_errors_are_exceptions():
     with pytest.raises(egnn.EgnnError):
         egnn.graph_wavelet_features(g, deltas=([9], [0], [1.0]))             # index out of range
     with pytest.raises(TypeError):
-        egnn.chebyshev_polynomials(c["lt"], 3, c["X0"])
+        egnn.chebyshev_polynomials(np.eye(4), 3, c["X0"])                    # neither an operator nor a scipy sparse matrix
 
 
 @pytest.mark.parametrize("name", ["kat_path", "cora_noloop", "cora_loops", "directed_weighted", "cora_wide8"])
