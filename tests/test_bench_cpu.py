@@ -38,3 +38,31 @@ def test_reference_arm_other_ranks_exit_quietly():
                           "--gpus", "2", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300,
                          cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_the_contract_line():
+    """The GPU arm on a small shape: one JSON line with the contract's keys, the roofline and the
+    end-to-end objects, and a config object identical to the reference arm's."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "pubmed", "--steps", "6",
+                          "--warmup", "3"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 6 and line["warmup"] >= 3 and line["value"] > 0
+    assert line["scaling"] == "strong" and line["vs_baseline"] is None and line["dtype"] == "f32"
+    r = line["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0 and 0 < r["frac"] < 1.2
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = line["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < line["value"]
+    assert line["gpu_launches"] > 0
+    ref = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "pubmed",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert ref.returncode == 0, ref.stderr[-2000:]
+    assert json.loads(ref.stdout.strip().splitlines()[-1])["config"] == line["config"]
