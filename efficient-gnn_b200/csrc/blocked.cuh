@@ -140,7 +140,7 @@ blocked_spmv_kernel(const __grid_constant__ BlockedParams p) {
                 const int lo_n = __shfl_sync(0xffffffffu, my_lo, r + 1), hi_n = __shfl_sync(0xffffffffu, my_hi, r + 1);
                 load4(lo_n + lane, hi_n, row + 1, cn, wn);
             }
-            // two-level sum (the oracle accumulates in float64): float32 over 64 entries per lane,
+            // two-level sum (the reference's scipy path accumulates in float64): float32 over 64 entries per lane,
             // those chunks and the 32 lanes in float64, always in the same order
             float acc = 0.f;
             double accd = 0.0;

@@ -461,6 +461,25 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base, const floa
     return EGNN_OK;
 }
 
+int egnn_patch_nodes(const float* w_base, const float* rowsum_base, const float* dinv_base, const uint8_t* iso_base,
+                     const float* x0_base, const float* y0_base, int64_t n, const int32_t* delta_row_host,
+                     const int32_t* delta_col_host, const float* delta_val_host, int32_t n_delta, float* dinv_io,
+                     uint8_t* iso_io, float* x0_io, float* y0_io, int32_t restore, egnn_stream_t stream) {
+    EGNN_REQUIRE(w_base && rowsum_base && dinv_base && iso_base && x0_base && y0_base && dinv_io && iso_io && x0_io && y0_io,
+                 "null pointer");
+    DeltaList d;
+    int rc = fill_delta(d, delta_row_host, delta_col_host, delta_val_host, n_delta);
+    if (rc) return rc;
+    for (int i = 0; i < n_delta; ++i)
+        EGNN_REQUIRE(d.row[i] >= 0 && d.row[i] < n && d.col[i] >= 0 && d.col[i] < n, "delta index out of range");
+    if (n_delta == 0) return EGNN_OK;
+    patch_nodes_kernel<<<1, 2 * EGNN_MAX_DELTA, 0, (cudaStream_t)stream>>>(w_base, rowsum_base, dinv_base, iso_base, x0_base,
+                                                                          y0_base, d, dinv_io, iso_io, x0_io, y0_io,
+                                                                          restore ? 1 : 0);
+    EGNN_LAUNCH_CHECK("patch_nodes_kernel launch");
+    return EGNN_OK;
+}
+
 static size_t row_order_cub_bytes(int64_t n) {
     size_t b = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr,

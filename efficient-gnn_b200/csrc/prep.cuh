@@ -244,4 +244,36 @@ __global__ void patch_degrees_kernel(const float* __restrict__ w_base,
     }
 }
 
+// UGCA recompute without the three vector copies: the scratch vectors dinv_io / iso_io / x0_io / y0_io hold
+// copies of the base graph's (made once per graph); mode 0 writes the patched values of every node a flip
+// touches (y0 = dinv * x0 included, so the step kernel needs no prologue phase), mode 1 puts the base
+// values back after the pass has been queued.  One thread per candidate node (rows, then columns of the
+// flips); the first occurrence of a node does the work.
+__global__ void __launch_bounds__(2 * EGNN_MAX_DELTA)
+patch_nodes_kernel(const float* __restrict__ w_base, const float* __restrict__ rowsum_base,
+                   const float* __restrict__ dinv_base, const uint8_t* __restrict__ iso_base,
+                   const float* __restrict__ x0_base, const float* __restrict__ y0_base, DeltaList d,
+                   float* __restrict__ dinv_io, uint8_t* __restrict__ iso_io, float* __restrict__ x0_io,
+                   float* __restrict__ y0_io, int mode) {
+    const int t = threadIdx.x;
+    if (t >= 2 * d.n) return;
+    const int u = t < d.n ? d.row[t] : d.col[t - d.n];
+    for (int j = 0; j < t; ++j)
+        if ((j < d.n ? d.row[j] : d.col[j - d.n]) == u) return;
+    if (mode == 1) {
+        dinv_io[u] = dinv_base[u]; iso_io[u] = iso_base[u]; x0_io[u] = x0_base[u]; y0_io[u] = y0_base[u];
+        return;
+    }
+    float dw = 0.f, dr = 0.f;
+    for (int j = 0; j < d.n; ++j) {
+        if (d.col[j] == u && d.row[j] != u) dw += d.val[j];     // in-degree (self loops excluded)
+        if (d.row[j] == u) dr += d.val[j];                      // row sum (self loops count)
+    }
+    float dv;
+    uint8_t is;
+    normaliser_from_w(w_base[u] + dw, dv, is);
+    const float x = (float)log1p((double)(rowsum_base[u] + dr));
+    dinv_io[u] = dv; iso_io[u] = is; x0_io[u] = x; y0_io[u] = dv * x;
+}
+
 }  // namespace egnn

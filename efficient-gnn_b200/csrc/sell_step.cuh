@@ -157,6 +157,7 @@ struct StepOrderView {            // pointers of one order, resolved once per CT
     float* tk;                    // or NULL
     int k, j;                     // order; index into the coefficient window
     bool first, last, push;
+    bool flips_here;              // an edge flip names a row of this CTA's epilogue range
 };
 
 __device__ __forceinline__ const float* step_t_ptr(const SellStepParams& p, int j) {
@@ -188,9 +189,10 @@ __device__ __forceinline__ StepRowPre step_row_prefetch(const SellStepParams& p,
 __device__ __forceinline__ void step_epilogue_finish(const SellStepParams& p, const StepOrderView& v, int i,
                                                      const StepRowPre& r, double accd) {
     const int gi = p.row0 + i;
-    for (int d = 0; d < p.delta.n; ++d)
-        if (p.delta.row[d] == gi && p.delta.col[d] != gi)
-            accd += (double)p.delta.val[d] * (double)__ldcg(v.operand + p.delta.col[d]);
+    if (v.flips_here)                     // some flip touches a row of this CTA (uniform per CTA; most CTAs skip the list)
+        for (int d = 0; d < p.delta.n; ++d)
+            if (p.delta.row[d] == gi && p.delta.col[d] != gi)
+                accd += (double)p.delta.val[d] * (double)__ldcg(v.operand + p.delta.col[d]);
     const float acc = (float)accd;
     const float lap = fmaf(r.theta, r.xprev, -p.a * r.di * acc);
     const float tk = v.first ? lap : fmaf(2.f, lap, -r.t2);
@@ -329,9 +331,12 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
         pending = true; pending_signal = true;
     }
 
+    bool flips_here = false;
+    for (int d = 0; d < p.delta.n; ++d) flips_here |= p.delta.row[d] - p.row0 >= r0 && p.delta.row[d] - p.row0 < r1;
+
     for (int k = p.order_begin; k <= p.order_end; ++k) {
         StepOrderView v;
-        v.k = k; v.j = k - p.order_begin;
+        v.k = k; v.j = k - p.order_begin; v.flips_here = flips_here;
         v.first = k == 1; v.last = k == p.k_max; v.push = k < p.k_max;
         const bool held = (k == p.order_begin) && p.operand_first != nullptr;
         v.operand = held ? p.operand_first : p.operand[(k - 1) & 1];

@@ -17,7 +17,7 @@ import torch
 
 from . import _cabi
 
-__all__ = ["CsrGraph", "as_graph", "enable_phase_stamps", "read_phase_stamps"]
+__all__ = ["CsrGraph", "as_graph", "deltas_from_dense", "enable_phase_stamps", "read_phase_stamps"]
 
 
 def _stream():
@@ -196,6 +196,7 @@ class CsrGraph:
         self.narrow_calls = 0      # F = 1 passes run on this graph (the plan is built on the second)
         self._row_order = None     # lazily built processing order of the wide kernel
         self._sorted = None        # lazily read result of the degree pass's sortedness check
+        self._scratch = None       # lazily built scratch copies of dinv / iso / x0 / y0 for the in-place UGCA patches
         self._y0 = None            # lazily built dinv * x0 (first operand of the narrow path, default signal)
 
     def _release_scratch(self):
@@ -298,6 +299,25 @@ class CsrGraph:
                 _cabi.ptr(dinv), _cabi.ptr(iso), _cabi.ptr(x0), 0, n, _stream()), "egnn_patch_degrees")
         return dinv, iso, x0
 
+    def patch_nodes(self, deltas, restore: bool = False):
+        """UGCA recompute loop: the degree vectors (and ``y0 = dinv * x0``) of the graph
+        with the flips applied, in persistent scratch vectors - only the touched entries
+        are written (``restore=True`` puts the base values back; queue it after the
+        pass that used them).  Returns ``(dinv, iso, x0, y0)``.  One pass at a time per graph."""
+        if self._scratch is None:
+            self._scratch = (self.dinv.clone(), self.iso.clone(), self.x0.clone(), self.y0().clone())
+        d_rows, d_cols, d_vals = deltas
+        lib = _cabi.load()
+        with torch.cuda.device(self.device):
+            _cabi.check(lib.egnn_patch_nodes(
+                _cabi.ptr(self.w), _cabi.ptr(self.rowsum), _cabi.ptr(self.dinv), _cabi.ptr(self.iso), _cabi.ptr(self.x0),
+                _cabi.ptr(self.y0()), self.n,
+                _cabi.host_array(C.c_int32, [int(v) for v in d_rows]),
+                _cabi.host_array(C.c_int32, [int(v) for v in d_cols]),
+                _cabi.host_array(C.c_float, [float(v) for v in d_vals]), len(d_rows),
+                *[_cabi.ptr(t) for t in self._scratch], 1 if restore else 0, _stream()), "egnn_patch_nodes")
+        return self._scratch
+
     def to_scipy(self):
         """Host copy as scipy CSR float32 (tests / oracle side only)."""
         import scipy.sparse as sp
@@ -377,6 +397,27 @@ def read_phase_stamps(plan, k: int, first_operand_in_kernel: bool = True):
         prev = st[i]; i += 1
     res["total"] = (prev - t0) / 1e3
     return res
+
+
+def deltas_from_dense(base_adj: torch.Tensor, adj: torch.Tensor, limit: int = 64):
+    """Edge flips that turn the dense adjacency ``base_adj`` into ``adj``:
+    ``(rows, cols, vals)`` with ``vals = adj - base_adj`` at the entries that
+    differ, or ``None`` when more than ``limit`` entries differ (EGNN_MAX_DELTA).
+
+    This is what lets the UNMODIFIED attack code (calib_attack/calib_fga.py:868,
+    908,952 calls ``surrogate(features, perturbed_adj)`` with a dense matrix and
+    never passes a flip list) take the no-rebuild path: one elementwise pass
+    over the two ``[N,N]`` tensors instead of dense->CSR + degree pass + a cold
+    first-use kernel.  Index plumbing only (torch ops)."""
+    if base_adj.shape != adj.shape or base_adj.device != adj.device:
+        return None
+    idx = torch.nonzero(adj != base_adj)                        # [D, 2]; synchronises (the count goes to the host)
+    if idx.shape[0] > limit:
+        return None
+    if idx.shape[0] == 0:
+        return ([], [], [])
+    vals = (adj[idx[:, 0], idx[:, 1]] - base_adj[idx[:, 0], idx[:, 1]]).to(torch.float32)
+    return (idx[:, 0].tolist(), idx[:, 1].tolist(), vals.tolist())
 
 
 def as_graph(adj, device="cuda") -> CsrGraph:

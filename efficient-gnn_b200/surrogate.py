@@ -27,7 +27,7 @@ import ctypes as C
 import torch
 
 from . import _cabi
-from .graph import CsrGraph, as_graph
+from .graph import CsrGraph, as_graph, deltas_from_dense
 
 __all__ = ["SparseGCNSurrogate", "StructureGradient"]
 
@@ -153,6 +153,12 @@ class SparseGCNSurrogate:
         of that loss is in :attr:`last_gradient`."""
         self.anchor = torch.zeros((), device=self.graph.device, requires_grad=True)
         return _TargetLogits.apply(self.anchor, self, int(target), deltas)
+
+    def flips_of(self, base_adj_dense, adj_dense):
+        """The delta list of a dense perturbed adjacency against the dense base the
+        surrogate was built from (``None`` if more than 64 entries differ) - for callers
+        that, like the reference attack, carry the perturbed graph as a dense matrix."""
+        return deltas_from_dense(base_adj_dense, adj_dense)
 
     def structure_gradient(self, loss, retain_graph=False):
         """Row / column ``target`` of ``dLoss/dA`` for a scalar ``loss`` computed from

@@ -23,7 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _cabi
-from .graph import CsrGraph, as_graph
+from .graph import CsrGraph, as_graph, deltas_from_dense
 
 __all__ = ["LaplacianOperator", "ExplicitOperator", "compute_normalized_laplacian", "chebyshev_polynomials",
            "graph_wavelet_features", "heat_coefficients", "WaveletResult", "WaveletSession", "WATS", "accuracy"]
@@ -55,10 +55,11 @@ class WaveletResult:
 
 def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_scale: float,
               op_shift: float, normalize: bool, want_orders: bool, deltas=None,
-              degree_vectors=None, order_events=None, use_sell=None, default_signal=False):
+              degree_vectors=None, order_events=None, use_sell=None, default_signal=False, y0=None):
     """One call of egnn_cheb_wavelet.  Returns (out [N,S,F], t_all or None).
     ``default_signal``: x0 is the graph's own log1p(degree) with its own degree
-    vectors, so the first operand dinv * x0 is the one cached on the graph."""
+    vectors, so the first operand dinv * x0 is the one cached on the graph; ``y0``: that
+    operand supplied by the caller (patched copy of the cached one, UGCA recompute)."""
     lib = _cabi.load()
     n, dev = graph.n, graph.device
     if x0.dim() == 1:
@@ -102,7 +103,7 @@ def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_
             _cabi.host_array(C.c_float, [float(v) for v in d_vals]), len(d_rows),
             _cabi.ptr(ws), ws_bytes, _stream(), order_events,
             None if plan is None else C.byref(plan), _cabi.ptr(row_order),
-            _cabi.ptr(graph.y0()) if (plan is not None and default_signal) else None,
+            _cabi.ptr(y0 if y0 is not None else graph.y0()) if (plan is not None and (default_signal or y0 is not None)) else None,
             blocked), "egnn_cheb_wavelet")
     return out, t_all
 
@@ -259,23 +260,36 @@ def graph_wavelet_features(adj_matrix, k=3, s=0.8, *, X0=None, lambda_max: float
     coeffs = heat_coefficients(k, s)
     degree_vectors = None
     x0 = graph.x0 if X0 is None else torch.as_tensor(X0)
+    y0 = None
     if deltas is not None and len(deltas[0]) > 0:
-        dinv, iso, x0_patched = graph.patched(*deltas)
+        # degree vectors of the flipped graph: only the touched entries of persistent scratch copies are
+        # written, and put back once the pass is queued (no copies of the N-vectors per perturbation)
+        dinv, iso, x0_patched, y0_patched = graph.patch_nodes(deltas)
         degree_vectors = (dinv, iso)
         if X0 is None:
-            x0 = x0_patched
+            x0, y0 = x0_patched, y0_patched
     else:
         deltas = None
     op_scale = 2.0 / float(lambda_max)
     default_signal = X0 is None and deltas is None
+    try:
+        return _wavelet_pass(graph, x0, k, coeffs, op_scale, normalize, return_parts, deltas, degree_vectors,
+                             _order_events, _use_sell, default_signal, y0)
+    finally:
+        if deltas is not None:
+            graph.patch_nodes(deltas, restore=True)
+
+
+def _wavelet_pass(graph, x0, k, coeffs, op_scale, normalize, return_parts, deltas, degree_vectors, _order_events,
+                  _use_sell, default_signal, y0):
     if return_parts:
         comb, t_all = _run_cheb(graph, x0, k, coeffs, op_scale, -1.0, False, True, deltas, degree_vectors,
-                                use_sell=_use_sell, default_signal=default_signal)
+                                use_sell=_use_sell, default_signal=default_signal, y0=y0)
         feats = comb / (comb.abs().sum(dim=2, keepdim=True) + 1e-8) if normalize else comb
         feats = feats.reshape(graph.n, -1)
         return WaveletResult(feats, [t_all[i] for i in range(k + 1)], comb)
     out, _ = _run_cheb(graph, x0, k, coeffs, op_scale, -1.0, normalize, False, deltas, degree_vectors,
-                       _order_events, _use_sell, default_signal)
+                       _order_events, _use_sell, default_signal, y0)
     return out.reshape(graph.n, -1)
 
 
@@ -351,6 +365,16 @@ class WATS(nn.Module):
                                           deltas=deltas)
         if adj is None:
             return self.wavelet_feats
+        # a dense adjacency that differs from the calibrator's own in a few entries (what the attack
+        # passes: calib_fga.py:897-908): take the flips and keep the resident graph and its plan
+        if isinstance(adj, torch.Tensor) and adj.layout == torch.strided and self.graph is not None \
+                and isinstance(self.adj, torch.Tensor) and adj.shape == self.adj.shape:
+            flips = deltas_from_dense(self.adj, adj.to(self.adj.device))
+            if flips is not None:
+                if not flips[0]:
+                    return self.wavelet_feats
+                return graph_wavelet_features(self.graph, k=self.k, s=self.s, lambda_max=self.lambda_max,
+                                              deltas=flips)
         return graph_wavelet_features(adj, k=self.k, s=self.s, lambda_max=self.lambda_max)
 
     def temperatures(self, wavelet_features):

@@ -118,6 +118,17 @@ int egnn_patch_degrees(const float* w_base, const float* rowsum_base,
                        float* dinv_out, uint8_t* iso_out, float* x0_out,
                        int64_t row_begin, int64_t n_rows, egnn_stream_t stream);
 
+/* The same patch without the three vector copies, for the recompute loop: the *_io vectors are
+ * scratch copies of the base graph's dinv / iso / x0 / y0 = dinv (.) x0 (made once by the caller);
+ * restore = 0 writes the patched values of every node a flip touches, restore = 1 puts the base
+ * values back (queue it after the wavelet pass that used the patched vectors).               */
+int egnn_patch_nodes(const float* w_base, const float* rowsum_base, const float* dinv_base,
+                     const uint8_t* iso_base, const float* x0_base, const float* y0_base, int64_t n,
+                     const int32_t* delta_row_host, const int32_t* delta_col_host,
+                     const float* delta_val_host, int32_t n_delta,
+                     float* dinv_io, uint8_t* iso_io, float* x0_io, float* y0_io,
+                     int32_t restore, egnn_stream_t stream);
+
 /* ---- SELL plan: one-time re-layout of a binary, column-sorted CSR -----------
  * New in this build (no reference counterpart: scipy streams plain CSR).  For
  * F = 1 - the reference's default signal, calibration/WATS.py:58-59 - the

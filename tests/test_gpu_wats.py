@@ -73,6 +73,10 @@ def test_recompute_on_forward_and_deltas():
         cal.recompute_on_forward = True
         by_dense = cal(x, pert)
     assert torch.allclose(by_delta, by_dense, atol=1e-5)
+    # the dense perturbed adjacency the unmodified attack passes (calib_fga.py:868,908) is recognised as
+    # a few flips of the calibrator's own graph: same no-rebuild path, bitwise the same features
+    assert torch.equal(cal.features_for(pert), cal.features_for(deltas=([target, j], [j, target], [v, v])))
+    assert torch.equal(cal.features_for(adj), cal.wavelet_feats)
     want = orc.wavelet_features(sp.csr_matrix(pert.cpu().numpy()), k=3, s=[0.4, 0.8]).astype(np.float32)
     got = cal.features_for(pert).cpu().numpy()
     np.testing.assert_allclose(got, want, atol=1e-6)
