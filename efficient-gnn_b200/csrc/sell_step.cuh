@@ -158,6 +158,7 @@ struct StepOrderView {            // pointers of one order, resolved once per CT
     int k, j;                     // order; index into the coefficient window
     bool first, last, push;
     bool flips_here;              // an edge flip names a row of this CTA's epilogue range
+    const float* flip_term;       // shared memory: contribution of every flip (0 for the ones of other CTAs' rows)
 };
 
 __device__ __forceinline__ const float* step_t_ptr(const SellStepParams& p, int j) {
@@ -191,8 +192,7 @@ __device__ __forceinline__ void step_epilogue_finish(const SellStepParams& p, co
     const int gi = p.row0 + i;
     if (v.flips_here)                     // some flip touches a row of this CTA (uniform per CTA; most CTAs skip the list)
         for (int d = 0; d < p.delta.n; ++d)
-            if (p.delta.row[d] == gi && p.delta.col[d] != gi)
-                accd += (double)p.delta.val[d] * (double)__ldcg(v.operand + p.delta.col[d]);
+            if (p.delta.row[d] == gi) accd += (double)v.flip_term[d];     // val * operand[col], fetched before the barrier wait
     const float acc = (float)accd;
     const float lap = fmaf(r.theta, r.xprev, -p.a * r.di * acc);
     const float tk = v.first ? lap : fmaf(2.f, lap, -r.t2);
@@ -229,6 +229,7 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
     extern __shared__ __align__(128) float ysm[];
     __shared__ __align__(8) unsigned long long stage_bar;
     __shared__ int hub_cnt;
+    __shared__ float flip_term[EGNN_MAX_DELTA];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int wid = tid >> 5;
@@ -336,7 +337,7 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
 
     for (int k = p.order_begin; k <= p.order_end; ++k) {
         StepOrderView v;
-        v.k = k; v.j = k - p.order_begin; v.flips_here = flips_here;
+        v.k = k; v.j = k - p.order_begin; v.flips_here = flips_here; v.flip_term = flip_term;
         v.first = k == 1; v.last = k == p.k_max; v.push = k < p.k_max;
         const bool held = (k == p.order_begin) && p.operand_first != nullptr;
         v.operand = held ? p.operand_first : p.operand[(k - 1) & 1];
@@ -438,6 +439,10 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
         StepRowPre pre_a{}, pre_b{};
         if (i_a < r1) pre_a = step_row_prefetch(p, v, i_a);
         if (i_b < r1) pre_b = step_row_prefetch(p, v, i_b);
+        if (flips_here && tid < p.delta.n) {                   // the flips' terms: the operand of this order is complete
+            const int lr = p.delta.row[tid] - p.row0, dc = p.delta.col[tid];
+            flip_term[tid] = (lr >= r0 && lr < r1 && dc != p.delta.row[tid]) ? p.delta.val[tid] * __ldcg(v.operand + dc) : 0.f;
+        }
         bar_wait();                                            // every partial sum of every row is in place
         stamp();
         // end-of-step signal: nobody reads the windows any more - unless edge flips are applied,
