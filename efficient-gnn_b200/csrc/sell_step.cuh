@@ -127,22 +127,25 @@ __device__ __forceinline__ void grid_wait(const unsigned long long* ctr, unsigne
     __threadfence();                      // acquire; also drops this SM's L1 lines of data other SMs rewrote
 }
 
-// One thread: wait until ranks p_lo..p_hi (except this one) have signalled `epoch` here.
+// Warp 0, every lane: wait until ranks p_lo..p_hi (except this one) have signalled `epoch`
+// here - one rank per lane, so the polls of several owners overlap.
 __device__ __forceinline__ void peer_wait_ranks(const unsigned* local_flags, int p_lo, int p_hi, int rank,
-                                                unsigned epoch, unsigned* error, bool stats) {
+                                                unsigned epoch, unsigned* error, bool stats, int lane) {
     const unsigned long long t0 = global_timer_ns();
-    for (int p = p_lo; p <= p_hi; ++p) {
+    for (int p = p_lo + lane; p <= p_hi; p += 32) {
         if (p == rank) continue;
         while ((int)(ld_relaxed_sys_u32(local_flags + p) - epoch) < 0) {
             __nanosleep(32);
             if (global_timer_ns() - t0 > kPeerTimeoutNs) {
                 atomicExch(error, 1u);
-                return;
+                break;
             }
         }
     }
-    __threadfence_system();               // acquire: the owners' operand stores are visible past this point
-    if (stats) {
+    __syncwarp();                         // every lane has seen its flag ...
+    if (lane == 0) __threadfence_system();    // ... one fence (32 of them cost ~10 us per order): acquire for what follows,
+    __syncwarp();                             // in every lane
+    if (stats && lane == 0) {
         unsigned long long* stat = reinterpret_cast<unsigned long long*>(
             reinterpret_cast<char*>(const_cast<unsigned*>(local_flags)) - kPeerFlagsOff + kPeerWaitNsOff);
         stat[0] += global_timer_ns() - t0;
@@ -266,19 +269,17 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
     unsigned signals = 0;                                      // flags this rank has raised in this launch
     unsigned stage_parity = 0;
     int stamp_i = 1;
-    bool waited_first = false;                                 // before the first store into the peers' windows
     bool pending = false, pending_signal = false;              // a barrier this CTA has arrived at but not yet waited for
     const bool late_done = PEER && p.delta.n > 0;              // the last epilogue reads the window (edge-flip corrections)
     __syncthreads();
 
-    // the peers may still be reading the buffers of the previous step: wait until every one of
-    // them has signalled its end (epoch_base counts this rank's own signals up to there)
-    auto wait_first = [&]() {
-        if (PEER && !waited_first) {
-            if (tid == 0) peer_wait_ranks(p.local_flags, 0, p.world - 1, p.rank, epoch_base, p.error, false);
-            __syncthreads();
-            waited_first = true;
-        }
+    // Before a phase stores into the windows: the buffer it writes was last read by the staging
+    // of the order before (or of the previous step), and a rank signals only after its grid
+    // barrier behind that staging - so every rank's latest signal must be in.  Ranks whose
+    // columns this rank's slices never touch are not waited for anywhere else.  Issued by warp 0
+    // before a __syncthreads (the flags are long up by then on balanced shards).
+    auto wait_windows_free = [&]() {
+        if (PEER && wid == 0) peer_wait_ranks(p.local_flags, 0, p.world - 1, p.rank, epoch_base + signals, p.error, false, lane);
     };
     // after a grid barrier that closed a producing phase: CTA 0 raises this rank's flag everywhere
     auto signal_peers = [&]() {
@@ -323,7 +324,8 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
 
     // ---- order 0: the first operand y_0 = dinv (.) T_0, unless the caller holds it -------------
     if (p.order_begin == 1 && p.operand_first == nullptr) {
-        wait_first();
+        wait_windows_free();
+        __syncthreads();
         for (int i = r0 + tid; i < r1; i += kSellThreads) {
             const float yv = __ldg(p.dinv + p.row0 + i) * __ldg(p.x0 + i);
             for (int d = 0; d < p.n_dst; ++d) p.ydst[0][d][p.row0 + i] = yv;
@@ -369,18 +371,20 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
             // stage the column block of the operand: bulk copies by one thread, tail and zero slots by the rest
             const float* src = v.operand + col0;
             const int cnt4 = cnt & ~3;
-            if (tid == 0) {
+            if (wid == 0) {
                 if (PEER && !held) {                           // written by the ranks owning these columns
                     const int p_lo = (int)(col0 / p.rows_per);
                     const int p_hi = (int)((col0 + cnt - 1) / p.rows_per);
                     peer_wait_ranks(p.local_flags, p_lo, min(p_hi, p.world - 1), p.rank, epoch_base + signals, p.error,
-                                    g == 0);
+                                    g == 0, lane);
                 }
-                fence_proxy_async();                           // generic-proxy writes (other CTAs / GPUs, acquired above) before the async-proxy reads
-                if (cnt4 > 0) {
-                    mbar_expect_tx(&stage_bar, (unsigned)cnt4 * 4u);
-                    for (int o = 0; o < cnt4; o += kStageChunkFloats)
-                        bulk_g2s(ysm + o, src + o, (unsigned)min(kStageChunkFloats, cnt4 - o) * 4u, &stage_bar);
+                if (lane == 0) {
+                    fence_proxy_async();                       // generic-proxy writes (other CTAs / GPUs, acquired above) before the async-proxy reads
+                    if (cnt4 > 0) {
+                        mbar_expect_tx(&stage_bar, (unsigned)cnt4 * 4u);
+                        for (int o = 0; o < cnt4; o += kStageChunkFloats)
+                            bulk_g2s(ysm + o, src + o, (unsigned)min(kStageChunkFloats, cnt4 - o) * 4u, &stage_bar);
+                    }
                 }
             }
             if (PEER && !held) __syncthreads();                // nobody touches the operand before the owners' flags are in
@@ -439,6 +443,13 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
         StepRowPre pre_a{}, pre_b{};
         if (i_a < r1) pre_a = step_row_prefetch(p, v, i_a);
         if (i_b < r1) pre_b = step_row_prefetch(p, v, i_b);
+        // (exchange) before this phase stores into the windows, and before a flip's term is read
+        // from a column whose owner none of this CTA's waits covered: every rank's latest signal.
+        // Polled by warp 0 while the grid barrier completes.
+        if (PEER && (v.push || flips_here)) {
+            wait_windows_free();
+            if (flips_here) __syncthreads();                   // uniform per CTA
+        }
         if (flips_here && tid < p.delta.n) {                   // the flips' terms: the operand of this order is complete
             const int lr = p.delta.row[tid] - p.row0, dc = p.delta.col[tid];
             flip_term[tid] = (lr >= r0 && lr < r1 && dc != p.delta.row[tid]) ? p.delta.val[tid] * __ldcg(v.operand + dc) : 0.f;
@@ -449,7 +460,6 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
         // whose corrections the last epilogue still reads from the operand (signalled after it)
         if (PEER && v.last && !late_done) signal_peers();
         if (g == 0 && tid < p.C) p.sched[tid * kSellCtrStride] = (unsigned)__ldg(p.cta_info + 2 * p.n_cta + tid);   // counters for the next SpMV phase
-        if (v.push) wait_first();
         for (int i = i_a; i < r1; i += kSellThreads) {
             const StepRowPre r = i == i_a ? pre_a : (i == i_b ? pre_b : step_row_prefetch(p, v, i));
             if (r.e - r.t > kEpiWarpRow) {

@@ -152,6 +152,60 @@ def test_two_rank_consecutive_steps_never_see_stale_operands(tmp_path):
     assert [open(tmp_path / f"rank{r}.txt").read() for r in range(2)] == ["0", "0"]
 
 
+def _lopsided_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    import efficient_gnn_b200 as egnn
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        # directed graph over 4 column blocks: the rows of rank 0 are long and point everywhere, the
+        # rows of rank 1 are short and point only at rank 1's own columns
+        cb = 49152
+        n, half, deg = 4 * cb, 2 * cb, 600
+        top = (np.arange(half, dtype=np.int64)[:, None] * 7 + np.arange(deg, dtype=np.int64)[None, :] * 327) % n
+        top.sort(axis=1)
+        low_deg = 40                                  # enough for the plan (8 entries per row and column block)
+        low = half + (np.arange(half, dtype=np.int64)[:, None] * 5 + np.arange(low_deg, dtype=np.int64)[None, :] * 1201) % half
+        low.sort(axis=1)
+        ci = torch.from_numpy(np.concatenate([top.ravel(), low.ravel()]).astype(np.int32))
+        rp = torch.from_numpy(np.concatenate([np.arange(half + 1, dtype=np.int64) * deg,
+                                              half * deg + low_deg * np.arange(1, half + 1, dtype=np.int64)]).astype(np.int32))
+        part = sharded.RowPartition(n, world)
+        assert part.rows_per == half
+        rpl, cil = part.slice_csr(rp, ci, rank)
+        sw = sharded.ShardedWavelet(rpl.to(dev), cil.to(dev), n, device=dev)
+        assert sw.plan is not None and sw.peer is not None
+        x_full = np.random.default_rng(9).standard_normal((n, 1)).astype(np.float32)
+        x = torch.from_numpy(x_full[sw.row_begin:sw.row_end]).to(dev)
+        g = egnn.CsrGraph(rp.to(dev), ci.to(dev), None, n)
+        want = egnn.graph_wavelet_features(g, k=8, s=0.8, X0=torch.from_numpy(x_full).to(dev), normalize=False)
+        want = want[sw.row_begin:sw.row_end]
+        worst = 0.0
+        for step in range(6):
+            got = sw.features(k=8, s=0.8, X0_local=x, normalize=False)
+            worst = max(worst, float((got - want).abs().max() / want.abs().max()))
+        sw.check_exchange()
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as fh:
+            fh.write(repr(worst))
+        sw.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_light_shard_never_overwrites_a_window_still_being_read(tmp_path):
+    """A rank whose slices touch none of a slower rank's columns is not held back by any operand
+    wait; before it stores the next operand into that rank's window it must still know that the
+    rank has finished staging the order that read the same buffer (K >= 4 reuses each buffer)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (one process per GPU)")
+    import torch.multiprocessing as mp
+    mp.spawn(_lopsided_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    worst = [float(open(tmp_path / f"rank{r}.txt").read()) for r in range(2)]
+    assert max(worst) <= 1e-5, worst
+
+
 def test_single_rank_window_is_a_plain_store(tmp_path):
     """world == 1: same kernels, no peers, no waits - must equal the NCCL-free path."""
     import torch.distributed as dist
