@@ -635,8 +635,9 @@ def run_ours(args, rank, local_rank, world):
         e_dt = (time.perf_counter() - t0) / e_steps
         e2e = {"value": work / e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e_dt * 1e3, "steps": e_steps, "entry": entry,
-               "note": "one-shot use of a fresh graph: generic CSR kernel (the SELL plan pays off from the second use of a "
-                       "graph on); the H2D copy of the CSR is ~80 % of the step"}
+               "note": "one-shot use of a fresh graph: the plan-free blocked kernel for large column-sorted graphs, else the "
+                       "generic CSR kernel (the SELL plan pays off from the second use of a graph on); the H2D copy of the "
+                       "CSR is ~85 % of the step"}
 
     # the reference's own code on the SAME graph (host copy of the resident CSR), one core like the reference
     cpu_baseline = None
