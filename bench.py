@@ -75,6 +75,10 @@ def parse_args():
     ap.add_argument("--no-wide", action="store_true", help="skip the roofline_wide sub-records")
     ap.add_argument("--no-ugca", action="store_true", help="skip the ugca sub-record")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
+    ap.add_argument("--node-order", choices=["random", "degree"], default="random",
+                    help="N > 1: 'degree' renumbers the synthetic graph by descending degree (skewed equal-rows shards)")
+    ap.add_argument("--balance", action="store_true",
+                    help="N > 1: renumber the nodes so that the equal-rows shards hold equal entries (sharded.BalancedOrder)")
     ap.add_argument("--entry", default="csr", choices=["csr", "dense"],
                     help="e2e entry: pinned host CSR (default) or the reference's own boundary, a dense [N,N] float32 "
                          "adjacency (calibration/WATS.py:99; small shapes only)")

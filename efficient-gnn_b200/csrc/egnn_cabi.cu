@@ -332,7 +332,7 @@ using namespace egnn;
 
 extern "C" {
 
-int egnn_abi_version(void) { return 4; }
+int egnn_abi_version(void) { return 5; }
 
 const char* egnn_last_error(void) { return last_error_buf(); }
 
@@ -961,6 +961,14 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
     rc = check_cuda(cudaMemcpyAsync(plan->rv_ptr, w.rv_ptr, 4 * (n + 1), cudaMemcpyDeviceToDevice, st), "copy rv_ptr"); if (rc) return rc;
     sell_cta_blocks_kernel<<<1, 32, 0, st>>>(w.slice_off, w.bsp, C, plan->n_cta, plan->cta_info, plan->sched);
     EGNN_LAUNCH_CHECK("sell_cta_blocks_kernel launch");
+    // epilogue row ranges balanced by cost (nvrow / nv of the workspace are free again: reused for the costs and their prefix)
+    sell_row_cost_kernel<<<(unsigned)ceil_div64(n + 1, 256), 256, 0, st>>>(w.rv_ptr, (int)n, w.nvrow);
+    EGNN_LAUNCH_CHECK("sell_row_cost_kernel launch");
+    size_t tb = w.cub_bytes;
+    rc = check_cuda(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, w.nvrow, w.nv, (int)(n + 1), st), "scan row costs"); if (rc) return rc;
+    sell_cta_rows_kernel<<<(unsigned)ceil_div64(plan->n_cta + 1, 128), 128, 0, st>>>(w.nv, (int)n, plan->n_cta,
+                                                                                 plan->cta_info + 2 * plan->n_cta + kSellMaxBlocks);
+    EGNN_LAUNCH_CHECK("sell_cta_rows_kernel launch");
     if (plan->n_slices > 0) {
         rc = check_cuda(cudaFuncSetAttribute(sell_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSellFillSmem),
                         "cudaFuncSetAttribute(sell_fill_kernel)");

@@ -171,7 +171,8 @@ sell_slice_kernel(int C, int lmax, const uint32_t* __restrict__ key_sorted,
 // order and the CTAs of a block share its slices dynamically.
 // cta_info: [n_cta] block (-1: none), [n_cta] rank of the CTA inside its block,
 // [kSellMaxBlocks] start value of the block's slice counter (32 x its CTAs: the
-// first slice of every warp is fixed).  sched: the counters themselves + the
+// first slice of every warp is fixed), [n_cta + 1] first row of every CTA's epilogue range
+// (sell_cta_rows_kernel).  sched: the counters themselves + the
 // grid-barrier counter, initialised here.
 __global__ void sell_cta_blocks_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ blk_slice_ptr,
                                        int C, int n_cta, int32_t* __restrict__ cta_info, unsigned* __restrict__ sched) {
@@ -214,6 +215,36 @@ __global__ void sell_cta_blocks_kernel(const int32_t* __restrict__ slice_off, co
         cta_info[2 * n_cta + c] = start;
         sched[c * kSellCtrStride] = (unsigned)start;
     }
+}
+
+// Row ranges of the epilogue phases, one per CTA, balanced by cost instead of by row count: a
+// row with more than kSellEpiWarpRow partial sums is summed by a whole warp and costs several
+// times a row a single thread finishes.  With random node ids the two agree; with ids sorted by
+// degree (or hubs clustered any other way) equal row counts left one CTA with every long row
+// and the grid barrier waiting for it (measured: +17 us per order on a degree-sorted Reddit shape).
+constexpr int kSellEpiWarpRow = 24;
+__global__ void sell_row_cost_kernel(const int32_t* __restrict__ rv_ptr, int n, int32_t* __restrict__ cost) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { cost[i] = 0; return; }
+    const int parts = rv_ptr[i + 1] - rv_ptr[i];
+    cost[i] = parts > kSellEpiWarpRow ? 28 + parts / 8 : 4;
+}
+
+// cta_rows[g] = first row of CTA g (g = 0 .. n_cta): the first row whose cost prefix reaches
+// g / n_cta of the total (cost_prefix = exclusive sums, [n + 1])
+__global__ void sell_cta_rows_kernel(const int32_t* __restrict__ cost_prefix, int n, int n_cta, int32_t* __restrict__ cta_rows) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_cta) return;
+    if (g == 0) { cta_rows[0] = 0; return; }
+    if (g == n_cta) { cta_rows[g] = n; return; }
+    const int64_t target = (int64_t)cost_prefix[n] * g / n_cta;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cost_prefix[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    cta_rows[g] = lo;
 }
 
 __global__ void sell_totals_kernel(const int32_t* __restrict__ slice_off, const int32_t* __restrict__ rv_ptr,

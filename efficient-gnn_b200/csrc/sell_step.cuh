@@ -34,7 +34,7 @@ namespace egnn {
 
 constexpr int kStepMaxOrders = 16;        // orders per launch (the coefficient window travels as kernel parameters)
 constexpr int kSchedBarrier = kSellMaxBlocks * kSellCtrStride;   // sched[c * 32]: next slice of column block c; then the 64-bit barrier counter
-constexpr int kEpiWarpRow = 24;           // rows with more partial sums than this are added up by a whole warp
+constexpr int kEpiWarpRow = kSellEpiWarpRow;           // rows with more partial sums than this are added up by a whole warp
 constexpr int kStageChunkFloats = 8192;   // one bulk copy = 32 KB
 
 struct SellStepParams {
@@ -252,8 +252,13 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
     const int col0 = c >= 0 ? c * p.CB : 0;
     const int cnt = c >= 0 ? min(p.CB, p.n_cols - col0) : 0;
     // rows this CTA owns in the epilogue phases (one or two per thread on the named shapes)
+#ifdef EGNN_EQUAL_EPILOGUE_ROWS                                                // A/B builds only
     const int r0 = (int)((int64_t)p.n_rows * g / p.n_cta);
     const int r1 = (int)((int64_t)p.n_rows * (g + 1) / p.n_cta);
+#else
+    const int r0 = __ldg(p.cta_info + 2 * p.n_cta + kSellMaxBlocks + g);       // ranges of equal cost (sell_cta_rows_kernel)
+    const int r1 = __ldg(p.cta_info + 2 * p.n_cta + kSellMaxBlocks + g + 1);
+#endif
 
     unsigned long long* bar_ctr = reinterpret_cast<unsigned long long*>(p.sched + kSchedBarrier);
     unsigned long long bar_base = 0;

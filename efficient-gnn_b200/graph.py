@@ -349,7 +349,7 @@ def build_sell_plan(rowptr: torch.Tensor, colidx: torch.Tensor, n_rows: int, n_c
             "idx": torch.empty(max(1, plan.n_entries), dtype=torch.int16, device=dev),
             "rv_ptr": torch.empty(n_rows + 1, dtype=torch.int32, device=dev),
             "vslot": torch.empty(max(1, plan.n_vrows), dtype=torch.int32, device=dev),
-            "cta_info": torch.empty(2 * plan.n_cta + 64, dtype=torch.int32, device=dev),
+            "cta_info": torch.empty(3 * plan.n_cta + 65, dtype=torch.int32, device=dev),
             "vpart": torch.empty(max(1, plan.n_rowv), dtype=torch.float32, device=dev),
             "sched": torch.zeros(64 * 32 + 64, dtype=torch.int32, device=dev),
         }

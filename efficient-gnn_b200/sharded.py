@@ -20,6 +20,7 @@ the product engine is :class:`CudaEngine` (C ABI, no fallback).
 from __future__ import annotations
 
 import ctypes as C
+import heapq
 import json
 import os
 import time
@@ -32,7 +33,7 @@ import torch.distributed as dist
 from . import _cabi
 from .wats import WIDE_MIN_F, heat_coefficients
 
-__all__ = ["RowPartition", "split_columns", "CudaEngine", "DistComm", "PeerExchange", "ShardedWavelet"]
+__all__ = ["RowPartition", "BalancedOrder", "split_columns", "CudaEngine", "DistComm", "PeerExchange", "ShardedWavelet"]
 
 
 class RowPartition:
@@ -56,6 +57,97 @@ class RowPartition:
         b, e = self.begin(rank), self.end(rank)
         lo, hi = int(rowptr[b]), int(rowptr[e])
         return (rowptr[b:e + 1] - rowptr[b]).to(torch.int32).contiguous(), colidx[lo:hi].contiguous()
+
+
+class BalancedOrder:
+    """Node relabelling that makes the equal-rows partition nnz-balanced.
+
+    The exchange addresses the operand by global node id and every rank owns one contiguous,
+    equally long id range (:class:`RowPartition`), so the entries per rank are balanced by
+    renumbering the nodes instead of moving the boundaries: nodes are handed to the ranks longest
+    row first, each to the rank with the fewest entries so far (LPT rule, within the fixed
+    length of every range), every rank keeps its nodes in their original relative order (what locality the ordering had inside a rank stays), and rank
+    r's nodes get the ids of its range.  The features are per node, so the result of the
+    relabelled graph is the original one with its rows permuted (:meth:`to_original`).
+    Orderings whose equal-rows shards are already balanced (random ids) gain nothing; a
+    degree-sorted or community-sorted ordering goes from the heaviest shard setting the step time
+    to equal shards.  Index plumbing only (torch ops on whatever device the CSR lives on).
+
+    ``perm[new] = old``, ``inv[old] = new``.
+    """
+
+    def __init__(self, perm: torch.Tensor, world: int):
+        self.perm = perm.to(torch.int64)
+        self.world = int(world)
+        self.n = int(perm.numel())
+        self.inv = torch.empty_like(self.perm)
+        self.inv[self.perm] = torch.arange(self.n, dtype=torch.int64, device=perm.device)
+
+    @classmethod
+    def from_rowptr(cls, rowptr: torch.Tensor, world: int) -> "BalancedOrder":
+        rp = rowptr.detach().to("cpu", torch.int64)
+        n = int(rp.numel()) - 1
+        part = RowPartition(n, world)
+        deg = rp[1:] - rp[:-1]
+        by_len = torch.argsort(deg, descending=True, stable=True).tolist()  # longest row first
+        deg_l = deg.tolist()
+        # longest-processing-time rule: the next-longest row goes to the rank with the fewest
+        # entries so far that still has room in its (fixed-length) id range; one pass over the
+        # nodes on the host, once per graph
+        heap = [(0, r) for r in range(world) if part.rows(r) > 0]
+        room = [part.rows(r) for r in range(world)]
+        owner_l = [0] * n
+        for node in by_len:
+            load, r = heapq.heappop(heap)
+            owner_l[node] = r
+            room[r] -= 1
+            if room[r] > 0:
+                heapq.heappush(heap, (load + deg_l[node], r))
+        owner = torch.tensor(owner_l, dtype=torch.int64)
+        perm = torch.argsort(owner * n + torch.arange(n, dtype=torch.int64))   # by (rank, original id)
+        return cls(perm.to(rowptr.device), world)
+
+    @staticmethod
+    def shard_entries(rowptr: torch.Tensor, world: int):
+        """Entries per rank of the equal-rows partition (to judge an ordering)."""
+        part = RowPartition(int(rowptr.numel()) - 1, world)
+        return [int(rowptr[part.end(r)]) - int(rowptr[part.begin(r)]) for r in range(world)]
+
+    def relabel_csr(self, rowptr: torch.Tensor, colidx: torch.Tensor, vals: Optional[torch.Tensor] = None):
+        """CSR of the relabelled graph: row ``new`` holds the entries of row ``perm[new]`` with
+        their columns renumbered, ascending (the narrow path needs column-sorted rows)."""
+        dev, n = rowptr.device, self.n
+        perm, inv = self.perm.to(dev), self.inv.to(dev)
+        counts = (rowptr[1:] - rowptr[:-1]).long()
+        rows_old = torch.repeat_interleave(torch.arange(n, device=dev), counts)
+        key = inv[rows_old] * n + inv[colidx.long()]
+        del rows_old
+        if vals is None:
+            key = key.sort().values
+            vals2 = None
+        else:
+            key, order = key.sort()
+            vals2 = vals[order].contiguous()
+        rowptr2 = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        rowptr2[1:] = torch.cumsum(counts[perm], 0)
+        return rowptr2.to(torch.int32), (key % n).to(torch.int32), vals2
+
+    def relabel_ids(self, ids):
+        """Original node ids -> ids of the relabelled graph (edge-flip lists, target nodes, masks' indices)."""
+        ids = torch.as_tensor(ids, dtype=torch.int64)
+        return self.inv.to(ids.device)[ids]
+
+    def relabel_deltas(self, deltas):
+        rows, cols, vals = deltas
+        return self.relabel_ids(rows).tolist(), self.relabel_ids(cols).tolist(), list(vals)
+
+    def from_original(self, x: torch.Tensor) -> torch.Tensor:
+        """Per-node rows in original order -> relabelled order (signals X0 going in)."""
+        return x[self.perm.to(x.device)]
+
+    def to_original(self, feats: torch.Tensor) -> torch.Tensor:
+        """Per-node rows in relabelled order -> original order (features coming out)."""
+        return feats[self.inv.to(feats.device)]
 
 
 def split_columns(rowptr: torch.Tensor, colidx: torch.Tensor, col_begin: int, col_end: int):
@@ -583,6 +675,25 @@ class ShardedWavelet:
 # --------------------------------------------------------------------------- #
 # bench.py entry for N > 1 (launched by torch.distributed.run)                   #
 # --------------------------------------------------------------------------- #
+def _bench_graph(args, dev, world):
+    """The named synthetic graph, optionally renumbered: ``--node-order degree`` sorts the nodes
+    by degree (the worst case for equal-rows shards; the generators' own ids are random),
+    ``--balance`` applies :class:`BalancedOrder` on top.  Returns the CSR and a record of the
+    entries per rank before / after."""
+    from . import synth
+    rp, ci, n = synth.synth_csr(args.workload, self_loops=True, device=dev)
+    info = {"node_order": getattr(args, "node_order", "random"), "balance": bool(getattr(args, "balance", False))}
+    if info["node_order"] == "degree":
+        deg = (rp[1:] - rp[:-1]).long()
+        by_deg = BalancedOrder(torch.argsort(deg, descending=True, stable=True), world)
+        rp, ci, _ = by_deg.relabel_csr(rp, ci)
+    info["shard_entries"] = BalancedOrder.shard_entries(rp, world)
+    if info["balance"]:
+        rp, ci, _ = BalancedOrder.from_rowptr(rp, world).relabel_csr(rp, ci)
+        info["shard_entries_balanced"] = BalancedOrder.shard_entries(rp, world)
+    return rp, ci, n, info
+
+
 def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, clock_sampler_cls,
                 physical_gpu_index, scale_list, workload_config, make_flips):
     from . import synth
@@ -595,7 +706,7 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
     scales = scale_list(n_scales)
     sh = synth.SHAPES[args.workload]
     # every rank generates the same seeded graph in its own HBM and keeps its rows
-    rp_full, ci_full, n = synth.synth_csr(args.workload, self_loops=True, device=dev)
+    rp_full, ci_full, n, ordering = _bench_graph(args, dev, world)
     nnz = int(ci_full.numel())
     part = RowPartition(n, world)
     rp_loc, ci_loc = part.slice_csr(rp_full, ci_full, rank)
@@ -698,7 +809,7 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
     if not getattr(args, "no_check", False):
         from .graph import CsrGraph
         from .wats import graph_wavelet_features
-        rp_full, ci_full, _ = synth.synth_csr(args.workload, self_loops=True, device=dev)
+        rp_full, ci_full, _, _ = _bench_graph(args, dev, world)
         gfull = CsrGraph(rp_full, ci_full, None, n)
         x_full = None
         if f > 1:
@@ -758,17 +869,20 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
     launches = torch.tensor([per_step_launches * args.steps if use_graph else sw.launches], device=dev,
                             dtype=torch.float64)
     dist.all_reduce(launches)
+    own_all = torch.zeros(1, device=dev, dtype=torch.float64)
+    if sw.plan is not None and f == 1:    # the kernels' own stream (2-byte indices), summed over the ranks' plans
+        own_all += float(2 * sw.plan.n_entries + 4 * (sw.plan.n_slices + 1) + 4 * sw.plan.n_vrows + 8 * sw.plan.n_rowv)
+    dist.all_reduce(own_all)
     if rank == 0:
         b_k = algorithmic_bytes(n, nnz, f, k_max, n_scales)
         peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
         peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.isfile(peaks) else 6650.0
         narrow = sw.plan is not None and f == 1
         fused = (sw.peer is not None and f == 1) or (sw.fused_wide and f >= WIDE_MIN_F)
-        if narrow:                    # the kernel's own stream (2-byte indices), summed over the ranks' plans
-            own = 2 * sw.plan.n_entries + 4 * (sw.plan.n_slices + 1) + 4 * sw.plan.n_vrows + 8 * sw.plan.n_rowv
-            own = float(own) * world * k_max          # shards are statistically equal: rank 0's plan x world
+        if narrow:
+            own = float(own_all.item()) * k_max
             achieved = own / (ms_per_step * 1e-3) / 1e9
-            model = "own stream of the step kernels (rank 0's plan x ranks x K), whole step incl. exchange"
+            model = "own stream of the step kernels (every rank's plan x K), whole step incl. exchange"
         else:
             achieved = sum(b_k) / (ms_per_step * 1e-3) / 1e9
             model = "SURVEY 8d contract bytes, whole step incl. exchange"
@@ -788,7 +902,8 @@ def bench_entry(args, rank, local_rank, world, metric, unit, algorithmic_bytes, 
                              else "csr-split-overlap"),
                     "exchange": "peer-window" if fused else "nccl-allgather", "cuda_graph": bool(use_graph),
                     "phase_us_rank0": phase_us,
-                    "per_rank_index_stream_mb": (2 * sw.plan.n_entries / 1e6) if narrow else 4 * nnz / world / 1e6},
+                    "per_rank_index_stream_mb": (2 * sw.plan.n_entries / 1e6) if narrow else 4 * nnz / world / 1e6,
+                    "ordering": ordering},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None,
                          "achieved_contract": sum(b_k) / (ms_per_step * 1e-3) / 1e9, "bytes_model": model},

@@ -140,7 +140,7 @@ int egnn_patch_nodes(const float* w_base, const float* rowsum_base, const float*
  *   egnn_sell_prepare    counts (all passes but the last) in `workspace`,
  *                        SYNCHRONISES the stream and fills the size fields;
  *   (caller allocates slice_off[n_slices+1], blk_slice_ptr[n_blocks+1],
- *    idx[n_entries] (uint16, 256-byte aligned), rv_ptr[n+1], vslot[n_vrows], cta_info[2*n_cta+64],
+ *    idx[n_entries] (uint16, 256-byte aligned), rv_ptr[n+1], vslot[n_vrows], cta_info[3*n_cta+65],
  *    sched[2112] uint32, vpart[n_rowv] float32 scratch: row i's partial sums are
  *    vpart[rv_ptr[i] .. rv_ptr[i+1]), virtual row v writes vpart[vslot[v]])
  *   egnn_sell_fill       writes the index stream; `workspace` must be the
@@ -157,8 +157,9 @@ typedef struct egnn_sell_plan {
     uint16_t* idx;
     int32_t* rv_ptr;
     int32_t* vslot;
-    int32_t* cta_info;                    /* [2 * n_cta + 64]: column block and rank inside it of every CTA, start value
-                                             of every block's slice counter (egnn_sell_fill)                          */
+    int32_t* cta_info;                    /* [3 * n_cta + 65]: column block and rank inside it of every CTA, start value
+                                             of every block's slice counter, first row of every CTA's epilogue range
+                                             (ranges of equal cost, not equal length) (egnn_sell_fill)                */
     float* vpart;
     uint32_t* sched;                      /* [2112] slice counters (one 128-byte line per column block) + grid-barrier
                                              counter of the step kernel (egnn_sell_fill

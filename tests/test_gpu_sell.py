@@ -108,6 +108,29 @@ def test_hub_rows_are_split_and_summed_deterministically():
         assert torch.equal(a, b)
 
 
+def test_degree_sorted_numbering_gets_epilogue_ranges_of_equal_cost():
+    """Node ids sorted by degree put every long row (many partial sums: summed by a warp) at the
+    front.  The plan's epilogue ranges are cut by cost: they cover every row once, the ones
+    holding the long rows are much shorter, and the result is the oracle's whatever the cut."""
+    from efficient_gnn_b200 import sharded
+    rp, ci, n = synth.synth_csr("physics", self_loops=True)
+    deg = (rp[1:] - rp[:-1]).long()
+    by_deg = sharded.BalancedOrder(torch.argsort(deg, descending=True, stable=True), 1)
+    rp, ci, _ = by_deg.relabel_csr(rp, ci)
+    adj = sp.csr_matrix((np.ones(ci.numel(), np.float32), ci.numpy(), rp.numpy()), shape=(n, n))
+    g = egnn.CsrGraph(rp.cuda(), ci.cuda(), None, n)
+    plan = g.sell_plan(force=True)
+    n_cta = plan.n_cta
+    rows = plan._keepalive["cta_info"].cpu().numpy()[2 * n_cta + 64: 3 * n_cta + 65]
+    assert rows[0] == 0 and rows[-1] == n and np.all(np.diff(rows) >= 0)
+    parts = np.diff(plan._keepalive["rv_ptr"].cpu().numpy())
+    if (parts > 24).any():                      # long rows exist and sit at the front: their ranges are shorter
+        assert np.diff(rows)[0] < np.diff(rows)[-1]
+    res = egnn.graph_wavelet_features(g, k=4, s=[0.8, 1.6], return_parts=True, _use_sell=True)
+    p = orc.wavelet_parts(adj, k=4, s=[0.8, 1.6])
+    check_parts(res, p["T"], p["S"], p["H"], "degree-sorted physics sell")
+
+
 def test_edge_flips_through_the_plan():
     c = load_case("cora_loops")
     dense = c["adj"].toarray()

@@ -254,3 +254,64 @@ def test_ranks_agree_on_the_narrow_path_gloo():
     ret = mp.Manager().dict()
     mp.spawn(_mixed_worker, args=(2, port, ret), nprocs=2, join=True)
     assert [ret.get(r) for r in range(2)] == ["no plan", "no plan"]
+
+
+def _skewed_csr(n=603, seed=3):
+    """Degree-sorted ids (longest rows first): equal-rows shards are badly unbalanced."""
+    rng = np.random.default_rng(seed)
+    deg = np.sort(np.minimum((rng.random(n) ** -0.7).astype(np.int64) + 1, 120))[::-1]
+    a = sp.lil_matrix((n, n), dtype=np.float32)
+    for i, d in enumerate(deg):
+        cols = rng.choice(n, size=int(d), replace=False)
+        a[i, cols] = 1.0
+        a[cols, i] = 1.0
+    a = sp.csr_matrix(a)
+    a.sort_indices()
+    return a
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_balanced_order_equalises_entries_and_keeps_the_features(world):
+    """SURVEY 8e (nnz-balanced shards): the relabelling leaves every rank the same number of
+    entries within one long row, fills every id range of the partition exactly, and the features
+    of the relabelled graph are the original ones with permuted rows."""
+    from efficient_gnn_b200 import sharded
+    from oracle import wats_oracle as orc
+    adj = _skewed_csr()
+    n = adj.shape[0]
+    rp = torch.from_numpy(adj.indptr.astype(np.int32))
+    ci = torch.from_numpy(adj.indices.astype(np.int32))
+    before = sharded.BalancedOrder.shard_entries(rp, world)
+    order = sharded.BalancedOrder.from_rowptr(rp, world)
+    assert sorted(order.perm.tolist()) == list(range(n))
+    rp2, ci2, _ = order.relabel_csr(rp, ci)
+    after = sharded.BalancedOrder.shard_entries(rp2, world)
+    assert sum(after) == sum(before) == adj.nnz
+    assert max(before) > 1.5 * min(before)
+    assert max(after) - min(after) <= int(np.diff(adj.indptr).max())
+    # rows stay column-sorted and the graph is the same up to the renumbering
+    adj2 = sp.csr_matrix((np.ones(adj.nnz, np.float32), ci2.numpy(), rp2.numpy()), shape=(n, n))
+    assert adj2.has_sorted_indices or (adj2.sort_indices() is None and np.array_equal(adj2.indices, ci2.numpy()))
+    p = order.perm.numpy()
+    assert (adj2 != adj[p][:, p]).nnz == 0
+    want = orc.wavelet_parts(adj, k=3, s=0.8)["S"][0]               # un-normalised (the F = 1 feature itself is a sign)
+    got = orc.wavelet_parts(adj2, k=3, s=0.8)["S"][0]
+    np.testing.assert_allclose(order.to_original(torch.from_numpy(np.asarray(got))).numpy(), want, atol=1e-12)
+    # ids going in (edge flips, signals) follow the same map
+    rows, cols, vals = order.relabel_deltas(([5, 9], [9, 5], [1.0, 1.0]))
+    assert p[rows[0]] == 5 and p[cols[0]] == 9 and vals == [1.0, 1.0]
+    x = torch.arange(n, dtype=torch.float32)
+    assert torch.equal(order.to_original(order.from_original(x)), x)
+
+
+def test_balanced_order_fills_short_last_ranges():
+    from efficient_gnn_b200 import sharded
+    for n, world in [(10, 4), (7, 8), (1, 3), (16, 4), (9, 2)]:
+        rp = torch.arange(n + 1, dtype=torch.int32) * 3
+        order = sharded.BalancedOrder.from_rowptr(rp, world)
+        assert sorted(order.perm.tolist()) == list(range(n))
+        weighted = torch.arange(n, 0, -1, dtype=torch.int64)          # with values as well
+        rp2, ci2, v2 = order.relabel_csr(torch.cat([torch.zeros(1, dtype=torch.int64), weighted.cumsum(0)]).int(),
+                                         torch.cat([torch.arange(d) % n for d in weighted.tolist()]).int(),
+                                         torch.arange(int(weighted.sum()), dtype=torch.float32))
+        assert int(rp2[-1]) == int(weighted.sum()) and v2.numel() == ci2.numel()
