@@ -1,7 +1,7 @@
 # equal-rows shards of a degree-sorted numbering, without and with sharded.BalancedOrder (N = $1, default 2)
 mkdir -p gpurun_out
 N=${1:-2}
-for cfg in "--workload reddit --node-order degree" "--workload reddit --node-order degree --balance" "--workload reddit --f 64 --node-order degree" "--workload reddit --f 64 --node-order degree --balance"; do
+for cfg in ${CFGS:-"--workload reddit --node-order degree" "--workload reddit --node-order degree --balance" "--workload reddit --f 64 --node-order degree" "--workload reddit --f 64 --node-order degree --balance"}; do
 tag=$(echo $cfg | tr -d ' -')
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 100 --warmup 5 --no-e2e $cfg > gpurun_out/bal_n${N}_$tag.log 2> gpurun_out/bal_n${N}_$tag.err; echo "bench N=$N $cfg rc=$?"
 python - <<PY

@@ -1,0 +1,17 @@
+# F = 1 only: degree-sorted numbering without / with BalancedOrder at N = $1 (default 2), and on one GPU
+mkdir -p gpurun_out
+N=${1:-2}
+for cfg in "--node-order degree" "--node-order degree --balance"; do
+tag=$(echo $cfg | tr -d ' -')
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 100 --warmup 5 --no-e2e $cfg > gpurun_out/balf1_n${N}_$tag.log 2> gpurun_out/balf1_n${N}_$tag.err; echo "bench N=$N $cfg rc=$?"
+python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/balf1_n${N}_$tag.log').read().strip().splitlines()[-1])
+    ph=d['run']['phase_us_rank0']
+    print('  ms/step', round(d['ms_per_step'],5), 'ugca', round(d['ugca']['recompute_ms'],5), 'check', d['check']['max_abs_diff_vs_single_gpu'], d['check'].get('ugca_max_abs_diff_vs_single_gpu'), 'err', d['exchange_error'], d['run']['ordering'])
+    print('  ', {k:v for k,v in ph.items() if k!='per_cta_us_after_order_opened_min_mean_max'})
+except Exception as e:
+    print('parse failed', e); print(open('gpurun_out/balf1_n${N}_$tag.err').read()[-1500:])
+PY
+done
