@@ -77,7 +77,8 @@ def _worker(rank, world, port, k, scales, steps, out_dir, f=1, flips=False):
     (3, 0.8, 1, 3, False), (4, [0.8, 1.6], 1, 12, False), (6, 0.8, 1, 8, False), (2, 0.8, 1, 8, False),
     (1, 0.8, 1, 3, False), (3, [0.8, 1.6], -1, 3, False), (4, 0.8, -1, 8, False),
     (3, [0.8, 1.6], 16, 3, False), (4, 0.8, 130, 3, False),
-    (3, 0.8, 1, 3, True), (4, [0.8, 1.6], 1, 4, True), (3, 0.8, 16, 3, True)])
+    (3, 0.8, 1, 3, True), (4, [0.8, 1.6], 1, 4, True), (3, 0.8, 16, 3, True),
+    (18, 0.8, 1, 3, False), (19, [0.8, 1.6], 1, 3, True)])                  # K > 16: two launches per step
 def test_two_rank_fused_exchange_matches_oracle(tmp_path, k, scales, f, steps, flips):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (one process per GPU)")
@@ -99,13 +100,14 @@ def test_two_rank_fused_exchange_matches_oracle(tmp_path, k, scales, f, steps, f
     want_h = np.concatenate(p["H"], axis=1).astype(np.float32)
     want_s = np.stack(p["S"], axis=1)                                   # [N, S, F]
     sure = np.concatenate([np.abs(sj) > 1e-4 * np.abs(sj).max() for sj in p["S"]], axis=1)
+    tol = 1e-5 if k <= 6 else 1e-4                                      # fp32 recurrence over many orders
     for rank in range(world):
         z = np.load(tmp_path / f"rank{rank}.npz")
         b, e = int(z["b"]), int(z["e"])
         for i in range(k + 1):
             ref = p["T"][i]
-            assert np.abs(z[f"t{i}"] - ref[b:e]).max() / np.abs(ref).max() <= 1e-5, f"order {i}"
-        assert np.abs(z["comb"] - want_s[b:e]).max() / np.abs(want_s).max() <= 1e-5
+            assert np.abs(z[f"t{i}"] - ref[b:e]).max() / np.abs(ref).max() <= tol, f"order {i}"
+        assert np.abs(z["comb"] - want_s[b:e]).max() / np.abs(want_s).max() <= tol
         for step in range(steps):
             got = z["fused"][step]
             np.testing.assert_allclose(got[sure[b:e]], want_h[b:e][sure[b:e]], atol=2e-5)

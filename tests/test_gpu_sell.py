@@ -131,6 +131,33 @@ def test_degree_sorted_numbering_gets_epilogue_ranges_of_equal_cost():
     check_parts(res, p["T"], p["S"], p["H"], "degree-sorted physics sell")
 
 
+@pytest.mark.parametrize("name,k", [("cora_loops", 20), ("pubmed_noloop", 33)])
+def test_more_orders_than_one_launch_holds(name, k):
+    """The step kernel runs 16 orders per launch: K > 16 continues in a second (third) launch
+    from the buffers the first left.  The first 16 orders must be bit-identical to a K = 16 pass,
+    every order must match the oracle (fp32 recurrence over K orders: 1e-4 of the order's
+    maximum), and the scale sums of all K + 1 orders must come out the same way."""
+    c = load_case(name)
+    g = egnn.CsrGraph.from_scipy(c["adj"])
+    assert g.sell_plan(force=True) is not None
+    scales = [0.8, 1.6]
+    long = egnn.graph_wavelet_features(g, k=k, s=scales, return_parts=True, _use_sell=True)
+    short = egnn.graph_wavelet_features(g, k=16, s=scales, return_parts=True, _use_sell=True)
+    assert len(long.orders) == k + 1
+    for a, b in zip(long.orders[:17], short.orders):
+        assert torch.equal(a, b)
+    p = orc.wavelet_parts(c["adj"], k=k, s=scales)
+    for i, (got, ref) in enumerate(zip(long.orders, p["T"])):
+        assert rel_max_err(got.cpu().numpy(), ref) <= 1e-4, f"order {i}"
+    for j, rs in enumerate(p["S"]):
+        assert rel_max_err(long.combined[:, j, :].cpu().numpy(), rs) <= 1e-4, f"S[{j}]"
+    generic = egnn.graph_wavelet_features(g, k=k, s=scales, return_parts=True, _use_sell=False)
+    for i, (a, b) in enumerate(zip(long.orders, generic.orders)):
+        assert rel_max_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-4, f"order {i} vs the generic kernel"
+    again = egnn.graph_wavelet_features(g, k=k, s=scales, _use_sell=True)
+    assert torch.equal(again, long.features)
+
+
 def test_edge_flips_through_the_plan():
     c = load_case("cora_loops")
     dense = c["adj"].toarray()
