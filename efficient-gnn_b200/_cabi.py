@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EGNN_LIB_PATH") or os.path.join(_HERE, "lib", "libegnn_b200.so")   # override: tuning builds
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # every symbol include/egnn_b200.h declares: name -> (restype, argtypes)
 _P, _I32, _I64, _F32, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -41,11 +41,11 @@ SYMBOLS = {
     "egnn_patch_nodes": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _P]),
     "egnn_cheb_workspace_bytes": (_SZ, [_I64, _I32]),
     "egnn_cheb_wavelet": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, _F32, _F32,
-                                    _P, _P, _I32, _P, _P, _P, _I32, _P, _SZ, _P, _P, _P, _P, _P, _I32]),
+                                    _P, _P, _I32, _P, _P, _P, _I32, _P, _SZ, _P, _P, _P, _P, _P, _I32, _P, _P, _I32]),
     "egnn_row_order_ws_bytes": (_SZ, [_I64]),
     "egnn_row_order": (C.c_int, [_P, _I64, _P, _P, _SZ, _P]),
     "egnn_sell_step_sharded": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P,
-                                         _F32, _F32, _I32, _P, _P, _P, _I32, _P, _P]),
+                                         _F32, _F32, _I32, _P, _P, _P, _I32, _P, _P, _I32, _P, _P]),
     "egnn_peer_window_bytes": (_SZ, [_I64, _I32, _I32]),
     "egnn_peer_alloc": (C.c_int, [_SZ, _P, _P]),
     "egnn_peer_open": (C.c_int, [_P, _P]),
@@ -150,3 +150,15 @@ def require_device():
     check(load().egnn_device_info(C.byref(sm), C.byref(major), C.byref(minor)), "egnn_device_info")
     _device_ok[dev] = (sm.value, major.value, minor.value)
     return _device_ok[dev]
+
+
+def current_stream():
+    """Raw handle of torch's current CUDA stream on the current device, as the ``egnn_stream_t``
+    argument of the C ABI.  ``torch.cuda.current_stream()`` costs ~15 us per call (device-index and
+    availability lookups); the recompute loop makes three library calls per step, so the raw getter
+    is used when this torch build has it."""
+    import torch
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return C.c_void_p(raw(torch.cuda.current_device()))
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

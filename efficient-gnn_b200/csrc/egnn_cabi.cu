@@ -284,7 +284,9 @@ static void step_fill_peer(SellStepParams& sp, const egnn_peer_window* w) {
 // waits on the other GPUs), one CTA per SM.
 static int launch_sell_step(const SellStepParams& sp, bool peer, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)sp.CB + kSellZeroSlots);
-    const void* fn = peer ? (const void*)sell_step_kernel<true> : (const void*)sell_step_kernel<false>;
+    const bool patch = sp.w_base != nullptr && sp.delta.n > 0;     // flips on top of the base graph's vectors
+    const void* fn = peer ? (patch ? (const void*)sell_step_kernel<true, true> : (const void*)sell_step_kernel<true, false>)
+                          : (patch ? (const void*)sell_step_kernel<false, true> : (const void*)sell_step_kernel<false, false>);
     int rc = check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                         "cudaFuncSetAttribute(sell_step_kernel)");
     if (rc) return rc;
@@ -332,7 +334,7 @@ using namespace egnn;
 
 extern "C" {
 
-int egnn_abi_version(void) { return 5; }
+int egnn_abi_version(void) { return 6; }
 
 const char* egnn_last_error(void) { return last_error_buf(); }
 
@@ -556,8 +558,11 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
                       const float* delta_val_host, int32_t n_delta, void* workspace,
                       size_t workspace_bytes, egnn_stream_t stream, void* const* order_events_host,
                       const egnn_sell_plan* sell_plan, const int32_t* row_order_or_null,
-                      const float* y0_or_null, int32_t rows_sorted) {
+                      const float* y0_or_null, int32_t rows_sorted,
+                      const float* w_base_or_null, const float* rowsum_base_or_null, int32_t default_signal) {
     EGNN_REQUIRE(rowptr && dinv && iso && x0 && out && coeffs_host, "null pointer");
+    EGNN_REQUIRE((w_base_or_null == nullptr) == (rowsum_base_or_null == nullptr), "w_base and rowsum_base come together");
+    EGNN_REQUIRE(w_base_or_null == nullptr || n_delta == 0 || sell_plan, "in-kernel degree patches need the SELL plan path");
     EGNN_REQUIRE(nnz == 0 || colidx, "null colidx");
     EGNN_REQUIRE(n >= 0 && n < (int64_t(1) << 31) && nnz >= 0 && nnz < (int64_t(1) << 31), "n/nnz out of int32 range");
     EGNN_REQUIRE(f >= 1, "f must be >= 1");
@@ -618,6 +623,7 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx, const float*
         SellStepParams sp{};
         step_fill_plan(sp, sell_plan);
         sp.delta = p.delta;
+        sp.w_base = w_base_or_null; sp.rowsum_base = rowsum_base_or_null; sp.patch_x0 = default_signal ? 1 : 0;
         sp.dinv = dinv; sp.iso = iso; sp.x0 = x0;
         sp.operand_first = y0_or_null;       // dinv (.) T_0 kept by the caller (fixed per graph for the default signal)
         sp.operand[0] = ybuf[0]; sp.operand[1] = ybuf[1];
@@ -988,8 +994,10 @@ int egnn_sell_step_sharded(const egnn_sell_plan* plan, const float* dinv_full, c
                            const float* coeffs_host, float op_scale, float op_shift, int32_t normalize_l1,
                            const int32_t* delta_row_host, const int32_t* delta_col_host,
                            const float* delta_val_host, int32_t n_delta,
+                           const float* w_base_or_null, const float* rowsum_base_or_null, int32_t default_signal,
                            const egnn_peer_window* win, egnn_stream_t stream) {
     EGNN_REQUIRE(plan && dinv_full && iso_full && out_local && coeffs_host, "null pointer");
+    EGNN_REQUIRE((w_base_or_null == nullptr) == (rowsum_base_or_null == nullptr), "w_base and rowsum_base come together");
     EGNN_REQUIRE(plan->vpart && plan->slice_off && plan->blk_slice_ptr && plan->rv_ptr && plan->vslot && plan->cta_info && plan->sched,
                  "SELL plan is not filled");
     EGNN_REQUIRE(order_begin >= 1 && order_begin <= order_end && order_end <= k_max && k_max <= EGNN_MAX_ORDER, "bad order range");
@@ -1015,6 +1023,7 @@ int egnn_sell_step_sharded(const egnn_sell_plan* plan, const float* dinv_full, c
         EGNN_REQUIRE(sp.delta.row[i] >= 0 && sp.delta.row[i] < plan->n_cols && sp.delta.col[i] >= 0 && sp.delta.col[i] < plan->n_cols,
                      "delta index out of range");
     step_fill_plan(sp, plan);
+    sp.w_base = w_base_or_null; sp.rowsum_base = rowsum_base_or_null; sp.patch_x0 = default_signal ? 1 : 0;
     sp.dinv = dinv_full; sp.iso = iso_full; sp.x0 = x0_local; sp.operand_first = y_first_full;
     sp.tbuf[0] = tbuf0; sp.tbuf[1] = tbuf1; sp.t_all = t_all_or_null; sp.out = out_local;
     sp.normalize = normalize_l1; sp.a = op_scale; sp.b = op_shift;

@@ -65,6 +65,11 @@ struct SellStepParams {
     float a, b;
     float coef[EGNN_MAX_SCALES][kStepMaxOrders + 1];   // coef[s][j] = c_{order_begin-1+j}(s)
     DeltaList delta;
+    // PATCH instantiation (UGCA recompute in one launch): dinv / iso / x0 / operand_first are the
+    // BASE graph's; the kernel re-derives the entries of the nodes the flips touch from these
+    const float* w_base;          // [n_cols] in-degree without self loops
+    const float* rowsum_base;     // [n_cols] row sums
+    int32_t patch_x0;             // 1: T_0 is the default signal log1p(row sum) and changes with the flips; 0: caller's signal, kept
     // exchange window of this rank (PEER instantiation)
     int32_t world, rank;
     int64_t rows_per;
@@ -162,7 +167,20 @@ struct StepOrderView {            // pointers of one order, resolved once per CT
     bool first, last, push;
     bool flips_here;              // an edge flip names a row of this CTA's epilogue range
     const float* flip_term;       // shared memory: contribution of every flip (0 for the ones of other CTAs' rows)
+    // PATCH: the nodes the flips touch (rows, then columns of the flips) and their re-derived vectors
+    bool touched_here;            // one of them is a row of this CTA's epilogue range
+    int n_touch;
+    const int* pt_node;
+    const float* pt_dinv;
+    const float* pt_x0;
+    const unsigned char* pt_iso;
 };
+
+__device__ __forceinline__ int step_patch_find(const int* node, int n, int gi) {
+    for (int j = 0; j < n; ++j)
+        if (node[j] == gi) return j;
+    return -1;
+}
 
 __device__ __forceinline__ const float* step_t_ptr(const SellStepParams& p, int j) {
     if (j == 0) return p.x0;
@@ -176,6 +194,7 @@ struct StepRowPre {
     float di, theta, xprev, t2, out0;
 };
 
+template <bool PATCH>
 __device__ __forceinline__ StepRowPre step_row_prefetch(const SellStepParams& p, const StepOrderView& v, int i) {
     StepRowPre r;
     const int gi = p.row0 + i;
@@ -186,6 +205,15 @@ __device__ __forceinline__ StepRowPre step_row_prefetch(const SellStepParams& p,
     r.xprev = v.tprev[i];
     r.t2 = v.first ? 0.f : v.tprev2[i];
     r.out0 = v.first ? 0.f : p.out[(size_t)i * p.S];
+    if (PATCH && v.touched_here) {        // a node an edge flip touches: its degree changed (uniform per CTA; most skip this)
+        const int j = step_patch_find(v.pt_node, v.n_touch, gi);
+        if (j >= 0) {
+            r.di = v.pt_dinv[j];
+            r.theta = fmaf(p.a, 1.f - (float)v.pt_iso[j], p.b);
+            if (v.k == 1) r.xprev = v.pt_x0[j];           // T_0 = x0 = log1p(row sum)
+            if (v.k == 2) r.t2 = v.pt_x0[j];
+        }
+    }
     return r;
 }
 
@@ -226,13 +254,16 @@ __device__ __forceinline__ double step_row_sum(const float* vpart, int t, int e)
     return a;
 }
 
-template <bool PEER>
+template <bool PEER, bool PATCH>
 __global__ void __launch_bounds__(kSellThreads, 1)
 sell_step_kernel(const __grid_constant__ SellStepParams p) {
     extern __shared__ __align__(128) float ysm[];
     __shared__ __align__(8) unsigned long long stage_bar;
     __shared__ int hub_cnt;
     __shared__ float flip_term[EGNN_MAX_DELTA];
+    __shared__ int pt_node[PATCH ? 2 * EGNN_MAX_DELTA : 1];
+    __shared__ float pt_dinv[PATCH ? 2 * EGNN_MAX_DELTA : 1], pt_x0[PATCH ? 2 * EGNN_MAX_DELTA : 1], pt_y0[PATCH ? 2 * EGNN_MAX_DELTA : 1];
+    __shared__ unsigned char pt_iso[PATCH ? 2 * EGNN_MAX_DELTA : 1];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int wid = tid >> 5;
@@ -276,6 +307,34 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
     int stamp_i = 1;
     bool pending = false, pending_signal = false;              // a barrier this CTA has arrived at but not yet waited for
     const bool late_done = PEER && p.delta.n > 0;              // the last epilogue reads the window (edge-flip corrections)
+    // PATCH: every CTA re-derives dinv / iso / x0 / dinv * x0 of the nodes the flips touch (the
+    // arithmetic of patch_nodes_kernel, prep.cuh) into shared memory - no patch / restore launches
+    // around the step and no patched copies of the vectors
+    const int n_touch = PATCH ? 2 * p.delta.n : 0;
+    bool touched_here = false;
+    if (PATCH) {
+        if (tid < n_touch) {
+            const int u = tid < p.delta.n ? p.delta.row[tid] : p.delta.col[tid - p.delta.n];
+            float dw = 0.f, dr = 0.f;
+            for (int j = 0; j < p.delta.n; ++j) {
+                if (p.delta.col[j] == u && p.delta.row[j] != u) dw += p.delta.val[j];     // in-degree (self loops excluded)
+                if (p.delta.row[j] == u) dr += p.delta.val[j];                            // row sum (self loops count)
+            }
+            float dv;
+            uint8_t is;
+            normaliser_from_w(__ldg(p.w_base + u) + dw, dv, is);
+            const int lr = u - p.row0;
+            float x = 0.f;                                     // a caller's signal is only ever needed for the own rows
+            if (p.patch_x0) x = (float)log1p((double)(__ldg(p.rowsum_base + u) + dr));
+            else if (lr >= 0 && lr < p.n_rows) x = __ldg(p.x0 + lr);
+            pt_node[tid] = u; pt_dinv[tid] = dv; pt_iso[tid] = is; pt_x0[tid] = x; pt_y0[tid] = dv * x;
+            if (p.t_all && p.order_begin == 1 && lr >= r0 && lr < r1) p.t_all[lr] = x;   // T_0 row handed back to the caller
+        }
+        for (int d = 0; d < p.delta.n; ++d) {
+            const int a = p.delta.row[d] - p.row0, b = p.delta.col[d] - p.row0;
+            touched_here |= (a >= r0 && a < r1) || (b >= r0 && b < r1);
+        }
+    }
     __syncthreads();
 
     // Before a phase stores into the windows: the buffer it writes was last read by the staging
@@ -332,7 +391,11 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
         wait_windows_free();
         __syncthreads();
         for (int i = r0 + tid; i < r1; i += kSellThreads) {
-            const float yv = __ldg(p.dinv + p.row0 + i) * __ldg(p.x0 + i);
+            float yv = __ldg(p.dinv + p.row0 + i) * __ldg(p.x0 + i);
+            if (PATCH && touched_here) {
+                const int j = step_patch_find(pt_node, n_touch, p.row0 + i);
+                if (j >= 0) yv = pt_y0[j];
+            }
             for (int d = 0; d < p.n_dst; ++d) p.ydst[0][d][p.row0 + i] = yv;
         }
         bar_arrive(PEER);
@@ -345,6 +408,8 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
     for (int k = p.order_begin; k <= p.order_end; ++k) {
         StepOrderView v;
         v.k = k; v.j = k - p.order_begin; v.flips_here = flips_here; v.flip_term = flip_term;
+        v.touched_here = touched_here; v.n_touch = n_touch;
+        v.pt_node = pt_node; v.pt_dinv = pt_dinv; v.pt_x0 = pt_x0; v.pt_iso = pt_iso;
         v.first = k == 1; v.last = k == p.k_max; v.push = k < p.k_max;
         const bool held = (k == p.order_begin) && p.operand_first != nullptr;
         v.operand = held ? p.operand_first : p.operand[(k - 1) & 1];
@@ -400,6 +465,13 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
             if (cnt4 > 0) mbar_wait(&stage_bar, stage_parity);
             stage_parity ^= (cnt4 > 0) ? 1u : 0u;
             __syncthreads();
+            if (PATCH && held && k == 1) {                     // the caller's dinv (.) x0 is the base graph's
+                if (tid < n_touch) {
+                    const int loc = pt_node[tid] - col0;
+                    if (loc >= 0 && loc < cnt) ysm[loc] = pt_y0[tid];
+                }
+                __syncthreads();
+            }
             trace();                                           // operand block staged
 
             while (s < bs1) {
@@ -446,8 +518,8 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
         if (tid == 0) hub_cnt = 0;
         const int i_a = r0 + tid, i_b = r0 + tid + kSellThreads;
         StepRowPre pre_a{}, pre_b{};
-        if (i_a < r1) pre_a = step_row_prefetch(p, v, i_a);
-        if (i_b < r1) pre_b = step_row_prefetch(p, v, i_b);
+        if (i_a < r1) pre_a = step_row_prefetch<PATCH>(p, v, i_a);
+        if (i_b < r1) pre_b = step_row_prefetch<PATCH>(p, v, i_b);
         // (exchange) before this phase stores into the windows, and before a flip's term is read
         // from a column whose owner none of this CTA's waits covered: every rank's latest signal.
         // Polled by warp 0 while the grid barrier completes.
@@ -457,7 +529,8 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
         }
         if (flips_here && tid < p.delta.n) {                   // the flips' terms: the operand of this order is complete
             const int lr = p.delta.row[tid] - p.row0, dc = p.delta.col[tid];
-            flip_term[tid] = (lr >= r0 && lr < r1 && dc != p.delta.row[tid]) ? p.delta.val[tid] * __ldcg(v.operand + dc) : 0.f;
+            const float yc = (PATCH && held && k == 1) ? pt_y0[p.delta.n + tid] : __ldcg(v.operand + dc);
+            flip_term[tid] = (lr >= r0 && lr < r1 && dc != p.delta.row[tid]) ? p.delta.val[tid] * yc : 0.f;
         }
         bar_wait();                                            // every partial sum of every row is in place
         stamp();
@@ -466,7 +539,7 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
         if (PEER && v.last && !late_done) signal_peers();
         if (g == 0 && tid < p.C) p.sched[tid * kSellCtrStride] = (unsigned)__ldg(p.cta_info + 2 * p.n_cta + tid);   // counters for the next SpMV phase
         for (int i = i_a; i < r1; i += kSellThreads) {
-            const StepRowPre r = i == i_a ? pre_a : (i == i_b ? pre_b : step_row_prefetch(p, v, i));
+            const StepRowPre r = i == i_a ? pre_a : (i == i_b ? pre_b : step_row_prefetch<PATCH>(p, v, i));
             if (r.e - r.t > kEpiWarpRow) {
                 const int h = atomicAdd(&hub_cnt, 1);
                 if (h < hub_cap) { hub_list[h] = i; continue; }
@@ -477,7 +550,7 @@ sell_step_kernel(const __grid_constant__ SellStepParams p) {
         const int n_hub = min(hub_cnt, hub_cap);
         for (int h = wid; h < n_hub; h += kWarps) {            // long rows: lane-strided float64 sums, fixed shuffle tree
             const int i = hub_list[h];
-            const StepRowPre r = step_row_prefetch(p, v, i);
+            const StepRowPre r = step_row_prefetch<PATCH>(p, v, i);
             double a = 0.0;
             for (int t = r.t + lane; t < r.e; t += 32) a += (double)__ldcg(p.vpart + t);
 #pragma unroll

@@ -21,7 +21,7 @@ __all__ = ["CsrGraph", "as_graph", "deltas_from_dense", "enable_phase_stamps", "
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _cabi.current_stream()
 
 
 class CsrGraph:

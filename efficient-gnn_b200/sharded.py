@@ -166,7 +166,7 @@ def split_columns(rowptr: torch.Tensor, colidx: torch.Tensor, col_begin: int, co
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _cabi.current_stream()
 
 
 def _delta_args(deltas):
@@ -251,9 +251,11 @@ class CudaEngine:
                                            _stream()), "egnn_prescale")
 
     def sell_step(self, plan, dinv, iso, x0, y_first_full, y_slabs, tbufs, t_all, out, order_begin, order_end, k_max,
-                  n_scales, coeffs, op_scale, op_shift, normalize, deltas=None, window=None):
+                  n_scales, coeffs, op_scale, op_shift, normalize, deltas=None, window=None, base_rowsum=None,
+                  default_signal=False):
         """Orders order_begin..order_end of the narrow path in one persistent launch
-        (include/egnn_b200.h ``egnn_sell_step_sharded``)."""
+        (include/egnn_b200.h ``egnn_sell_step_sharded``).  ``base_rowsum`` (full length): the
+        vectors passed are the base graph's and the kernel applies the flips' degree patches itself."""
         ys = (None, None) if y_slabs is None else y_slabs
         tb = (None, None) if tbufs is None else tbufs
         _cabi.check(self.lib.egnn_sell_step_sharded(
@@ -261,6 +263,8 @@ class CudaEngine:
             _cabi.ptr(ys[0]), _cabi.ptr(ys[1]), _cabi.ptr(tb[0]), _cabi.ptr(tb[1]), _cabi.ptr(t_all), _cabi.ptr(out),
             order_begin, order_end, k_max, n_scales, coeffs.ctypes.data_as(C.c_void_p), float(op_scale),
             float(op_shift), 1 if normalize else 0, *_delta_args(deltas),
+            _cabi.ptr(self.w_full) if base_rowsum is not None else None, _cabi.ptr(base_rowsum),
+            1 if default_signal else 0,
             None if window is None else C.byref(window), _stream()), "egnn_sell_step_sharded")
 
     def peer_prescale_push(self, x_local, dinv, n_rows, row0, f, window):
@@ -458,7 +462,7 @@ class ShardedWavelet:
         self.fused_wide = borrowed.fused_wide if borrowed is not None else bool(real_group and peer_exchange)
         # default signal X0 = log1p(degree): every rank keeps the whole pre-scaled vector (one
         # all-gather at build time), so order 1 of the fused narrow path needs no exchange
-        self.y0_full = None
+        self.y0_full = self._rowsum_full = None
         if self.peer is not None and self.world > 1:
             rp_ = self.part.rows_per
             pad = torch.zeros(rp_, dtype=torch.float32, device=self.device)
@@ -466,6 +470,14 @@ class ShardedWavelet:
             full = torch.empty(self.world * rp_, dtype=torch.float32, device=self.device)
             self._allgather(full, pad)
             self.y0_full = (self.dinv * full[:self.n]).contiguous()
+            # and the row sums of every node, so that each rank can re-derive the vectors of any node
+            # an edge flip touches without an exchange (UGCA recompute, features(deltas=...))
+            rowsum_local = getattr(self.engine, "rowsum_local", None)
+            if rowsum_local is not None and isinstance(self.engine, CudaEngine):
+                pad = torch.zeros(rp_, dtype=torch.float32, device=self.device)
+                pad[:self.rows] = rowsum_local
+                self._allgather(full, pad)
+                self._rowsum_full = full[:self.n].clone()
         self.launches = 0
 
     def _wide_window(self, ldy: int):
@@ -527,9 +539,18 @@ class ShardedWavelet:
         coeffs = np.ascontiguousarray(heat_coefficients(k, s), dtype=np.float32)
         n_scales = coeffs.shape[0]
         dinv, iso, x0_default = self.dinv, self.iso, self.x0
+        base_rowsum = None
         if deltas is not None and len(deltas[0]) > 0:
-            dinv, iso, x0_default = eng.patch_degrees(self.dinv, self.iso, self.x0, self.n, self.row_begin, self.rows,
-                                                      deltas)
+            x_in = None if X0_local is None else torch.as_tensor(X0_local)
+            f_in = 1 if (x_in is None or x_in.dim() == 1) else int(x_in.shape[1])
+            if k >= 1 and f_in == 1 and self.plan is not None and self.peer is not None and self._rowsum_full is not None:
+                # fused narrow path: the step kernel gets the base graph's vectors plus the row sums of every
+                # node and re-derives the nodes the flips touch itself (same arithmetic on every rank) - a
+                # perturbed pass is one launch, and the first operand dinv * x0 stays known everywhere
+                base_rowsum = self._rowsum_full
+            else:
+                dinv, iso, x0_default = eng.patch_degrees(self.dinv, self.iso, self.x0, self.n, self.row_begin,
+                                                          self.rows, deltas)
         else:
             deltas = None
         x0 = x0_default.reshape(-1, 1) if X0_local is None else torch.as_tensor(X0_local)
@@ -597,9 +618,9 @@ class ShardedWavelet:
             if fused:
                 # the whole step is ONE launch: operands travel through the exchange windows, the
                 # kernel waits on the owners' flags per column block and signals from its epilogue
-                y0 = self.y0_full if (X0_local is None and deltas is None) else None
+                y0 = self.y0_full if X0_local is None and (deltas is None or base_rowsum is not None) else None
                 eng.sell_step(self.plan, dinv, iso, x0, y0, None, tbufs, t_all, out, 1, k, *tail,
-                              window=self.peer.window)
+                              window=self.peer.window, base_rowsum=base_rowsum, default_signal=X0_local is None)
                 self.launches += 1
             elif self.world == 1:
                 y_slabs = (torch.empty(self.n, dtype=torch.float32, device=dev),
@@ -618,6 +639,8 @@ class ShardedWavelet:
                         eng.sell_step(self.plan, dinv, iso, x0, full, y_slabs, tbufs, t_all, out, order, order, *tail)
                         self.launches += 1
             if return_parts:
+                if base_rowsum is not None:       # T_0 of the flipped graph: the kernel wrote the touched rows
+                    orders[0] = t_all[0, :self.rows].reshape(-1, 1)
                 orders += [t_all[i, :self.rows].reshape(-1, 1) for i in range(1, k + 1)]
             return finish(out, orders)
         # generic CSR kernel, local / remote column halves around the exchange of T_{k-1}

@@ -35,7 +35,7 @@ CTX_FLOATS = 136
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _cabi.current_stream()
 
 
 def _delta_args(deltas):

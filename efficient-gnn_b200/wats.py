@@ -30,7 +30,7 @@ __all__ = ["LaplacianOperator", "ExplicitOperator", "compute_normalized_laplacia
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _cabi.current_stream()
 
 
 WIDE_MIN_F = 8       # signals at least this wide run on the wide-row kernel (csrc/wide.cuh)
@@ -55,11 +55,15 @@ class WaveletResult:
 
 def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_scale: float,
               op_shift: float, normalize: bool, want_orders: bool, deltas=None,
-              degree_vectors=None, order_events=None, use_sell=None, default_signal=False, y0=None):
+              degree_vectors=None, order_events=None, use_sell=None, default_signal=False, y0=None,
+              patch_in_kernel=False):
     """One call of egnn_cheb_wavelet.  Returns (out [N,S,F], t_all or None).
     ``default_signal``: x0 is the graph's own log1p(degree) with its own degree
     vectors, so the first operand dinv * x0 is the one cached on the graph; ``y0``: that
-    operand supplied by the caller (patched copy of the cached one, UGCA recompute)."""
+    operand supplied by the caller (patched copy of the cached one, UGCA recompute).
+    ``patch_in_kernel``: ``deltas`` come with the BASE graph's vectors; on the SELL plan path the
+    step kernel re-derives the touched nodes itself (one launch per perturbed pass) - callers
+    check :func:`_patches_in_kernel` first."""
     lib = _cabi.load()
     n, dev = graph.n, graph.device
     if x0.dim() == 1:
@@ -104,8 +108,20 @@ def _run_cheb(graph: CsrGraph, x0: torch.Tensor, k: int, coeffs: np.ndarray, op_
             _cabi.ptr(ws), ws_bytes, _stream(), order_events,
             None if plan is None else C.byref(plan), _cabi.ptr(row_order),
             _cabi.ptr(y0 if y0 is not None else graph.y0()) if (plan is not None and (default_signal or y0 is not None)) else None,
-            blocked), "egnn_cheb_wavelet")
+            blocked,
+            _cabi.ptr(graph.w) if patch_in_kernel else None, _cabi.ptr(graph.rowsum) if patch_in_kernel else None,
+            1 if default_signal else 0), "egnn_cheb_wavelet")
     return out, t_all
+
+
+def _patches_in_kernel(graph: CsrGraph, f: int, k: int, use_sell) -> bool:
+    """Will a perturbed pass of this shape run on the SELL plan (whose kernel applies the degree
+    patches of the flips itself)?  Mirrors the plan choice of :func:`_run_cheb`."""
+    if f != 1 or k < 1 or use_sell is False or use_sell == "blocked":
+        return False
+    if use_sell or graph.narrow_calls >= 1 or graph.has_sell_plan():
+        return graph.sell_plan(force=bool(use_sell)) is not None
+    return False
 
 
 class LaplacianOperator:
@@ -261,35 +277,40 @@ def graph_wavelet_features(adj_matrix, k=3, s=0.8, *, X0=None, lambda_max: float
     degree_vectors = None
     x0 = graph.x0 if X0 is None else torch.as_tensor(X0)
     y0 = None
+    in_kernel = False
     if deltas is not None and len(deltas[0]) > 0:
-        # degree vectors of the flipped graph: only the touched entries of persistent scratch copies are
-        # written, and put back once the pass is queued (no copies of the N-vectors per perturbation)
-        dinv, iso, x0_patched, y0_patched = graph.patch_nodes(deltas)
-        degree_vectors = (dinv, iso)
-        if X0 is None:
-            x0, y0 = x0_patched, y0_patched
+        in_kernel = _patches_in_kernel(graph, 1 if x0.dim() == 1 else int(x0.shape[1]), k, _use_sell)
+        if not in_kernel:
+            # degree vectors of the flipped graph: only the touched entries of persistent scratch copies are
+            # written, and put back once the pass is queued (no copies of the N-vectors per perturbation)
+            dinv, iso, x0_patched, y0_patched = graph.patch_nodes(deltas)
+            degree_vectors = (dinv, iso)
+            if X0 is None:
+                x0, y0 = x0_patched, y0_patched
+        # else (SELL plan): the step kernel re-derives the touched nodes from the base vectors - one launch
     else:
         deltas = None
     op_scale = 2.0 / float(lambda_max)
-    default_signal = X0 is None and deltas is None
+    default_signal = X0 is None and (deltas is None or in_kernel)
     try:
         return _wavelet_pass(graph, x0, k, coeffs, op_scale, normalize, return_parts, deltas, degree_vectors,
-                             _order_events, _use_sell, default_signal, y0)
+                             _order_events, _use_sell, default_signal, y0, in_kernel)
     finally:
-        if deltas is not None:
+        if deltas is not None and not in_kernel:
             graph.patch_nodes(deltas, restore=True)
 
 
 def _wavelet_pass(graph, x0, k, coeffs, op_scale, normalize, return_parts, deltas, degree_vectors, _order_events,
-                  _use_sell, default_signal, y0):
+                  _use_sell, default_signal, y0, patch_in_kernel=False):
     if return_parts:
         comb, t_all = _run_cheb(graph, x0, k, coeffs, op_scale, -1.0, False, True, deltas, degree_vectors,
-                                use_sell=_use_sell, default_signal=default_signal, y0=y0)
+                                use_sell=_use_sell, default_signal=default_signal, y0=y0,
+                                patch_in_kernel=patch_in_kernel)
         feats = comb / (comb.abs().sum(dim=2, keepdim=True) + 1e-8) if normalize else comb
         feats = feats.reshape(graph.n, -1)
         return WaveletResult(feats, [t_all[i] for i in range(k + 1)], comb)
     out, _ = _run_cheb(graph, x0, k, coeffs, op_scale, -1.0, normalize, False, deltas, degree_vectors,
-                       _order_events, _use_sell, default_signal, y0)
+                       _order_events, _use_sell, default_signal, y0, patch_in_kernel)
     return out.reshape(graph.n, -1)
 
 

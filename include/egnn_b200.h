@@ -212,7 +212,14 @@ int egnn_sell_fill(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
  * flag of egnn_graph_prep): f == 1 without a plan on a large graph (nnz >= 4 M)
  * then runs the plan-free column-blocked kernel (csrc/blocked.cuh: operand
  * staged in shared memory, no re-layout) instead of the generic CSR kernel
- * (2: also on small graphs - tests).                                          */
+ * (2: also on small graphs - tests).
+ * w_base_or_null / rowsum_base_or_null (SELL plan + edge flips): the base
+ * graph's in-degrees without self loops and row sums [n] (the `w` and `rowsum`
+ * of egnn_graph_prep).  When given, dinv / iso / x0 / y0_or_null are the BASE
+ * graph's vectors and the step kernel re-derives the entries of the nodes the
+ * flips touch itself (the arithmetic of egnn_patch_nodes): a perturbed pass is
+ * one launch, nothing to patch or restore.  default_signal != 0 says that x0
+ * is log1p(row sum) and changes with the flips; 0 keeps the caller's x0.     */
 size_t egnn_cheb_workspace_bytes(int64_t n, int32_t f);
 int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx,
                       const float* vals_or_null, const float* dinv,
@@ -225,7 +232,9 @@ int egnn_cheb_wavelet(const int32_t* rowptr, const int32_t* colidx,
                       void* workspace, size_t workspace_bytes,
                       egnn_stream_t stream, void* const* order_events_host,
                       const egnn_sell_plan* sell_plan_or_null, const int32_t* row_order_or_null,
-                      const float* y0_or_null, int32_t rows_sorted);
+                      const float* y0_or_null, int32_t rows_sorted,
+                      const float* w_base_or_null, const float* rowsum_base_or_null,
+                      int32_t default_signal);
 
 /* Processing order of the wide-signal kernel (new in this build): rows by
  * descending stored-entry count.  order_out: int32[n + 1] - the permutation,
@@ -364,7 +373,10 @@ int egnn_peer_wait_stats(const egnn_peer_window* win, uint64_t* total_ns, uint64
  *   t_all_or_null   [k_max+1, rows]: every order stored (then tbuf* unused);
  *                   the caller fills row block 0 with T_0
  *   delta_*         edge flips (GLOBAL row/col ids, host arrays) applied on
- *                   top of the plan; dinv/iso/x0 must describe the perturbed graph
+ *                   top of the plan; dinv/iso/x0 must describe the perturbed graph -
+ *                   or, with w_base_or_null / rowsum_base_or_null [n_cols] given
+ *                   (see egnn_cheb_wavelet), the base graph: the kernel then
+ *                   re-derives the touched nodes itself, on every rank alike
  * With win_or_null (world > 1) the exchange is fused and the whole step is one
  * call (order_begin = 1, order_end = k_max): before staging a column block the
  * kernel waits for the flags of the ranks that own those columns, the epilogue
@@ -386,6 +398,8 @@ int egnn_sell_step_sharded(const egnn_sell_plan* plan, const float* dinv_full,
                            float op_shift, int32_t normalize_l1,
                            const int32_t* delta_row_host, const int32_t* delta_col_host,
                            const float* delta_val_host, int32_t n_delta,
+                           const float* w_base_or_null, const float* rowsum_base_or_null,
+                           int32_t default_signal,
                            const egnn_peer_window* win_or_null, egnn_stream_t stream);
 
 /* y[r, :] = dinv_full[row0 + r] * x[r, :]: the gather operand of order 1 on

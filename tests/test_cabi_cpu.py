@@ -34,7 +34,8 @@ def test_library_exports_every_declared_symbol():
 def test_invalid_arguments_return_status_not_crash():
     lib = _cabi.load()
     rc = lib.egnn_cheb_wavelet(None, None, None, None, None, None, 4, 4, 1, 3, 1, None, 1.0, -1.0,
-                               None, None, 1, None, None, None, 0, None, 0, None, None, None, None, None, 0)
+                               None, None, 1, None, None, None, 0, None, 0, None, None, None, None, None, 0,
+                               None, None, 0)
     assert rc == -1
     assert b"null pointer" in lib.egnn_last_error()
     with pytest.raises(_cabi.EgnnError):
