@@ -541,6 +541,10 @@ def run_ours(args, rank, local_rank, world):
                            "note": "operand staging + slices + closing grid barrier of one order, from the kernel's own "
                                    "globaltimer stamps (last launch of the timed region)"},
             "kernel_share_of_step": launch_ms / ms_per_step,
+            # the events bracket a graph replay of the cooperative launch and include its launch latency
+            # (share of step > 1); the kernel's own clock from its first to its last instruction:
+            "kernel_clock_ms": phases["total"] * 1e-3,
+            "frac_by_kernel_clock": sum(own) / (phases["total"] * 1e-6) / 1e9 / peak,
             "padded_entries": int(plan.n_entries), "virtual_rows": int(plan.n_rowv),
         }
         launches_per_step = (k_max + 15) // 16 + (1 if flips is not None else 0)
