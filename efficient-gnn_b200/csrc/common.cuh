@@ -50,12 +50,6 @@ __device__ __forceinline__ int ld_stream_i32(const int* p) {
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ int4 ld_stream_i32x4(const int4* p) {
-    int4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ float ld_stream_f32(const float* p) {
     float v;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));

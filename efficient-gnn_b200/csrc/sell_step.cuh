@@ -104,14 +104,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsign
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // Grid barrier of the cooperative launch, split in two halves so that work which does not
 // depend on the other CTAs runs between them.  One 64-bit counter that only grows: barrier

@@ -52,6 +52,3 @@ def elementwise_ratio(got, ref, tol=1e-5, floor=None):
     floor = (ELEMENT_FLOOR if floor is None else floor) * np.abs(ref).max()
     return float((np.abs(got - ref) / (tol * np.maximum(np.abs(ref), floor) + 1e-300)).max())
 
-
-def elementwise_ok(got, ref, tol=1e-5):
-    return elementwise_ratio(got, ref, tol) <= 1.0

@@ -1,7 +1,6 @@
 """Stand-in base models for the downstream parity tests (written for this
 repo; the parameter creation order matches the reference's CompatibleGCN,
 src/gnn/model.py:24-41, so a shared seed gives identical initial weights)."""
-import torch
 import torch.nn.functional as F
 from torch import nn
 

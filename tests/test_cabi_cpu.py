@@ -1,7 +1,6 @@
 """No-GPU checks of the boundary: the shared library loads, exports every
 symbol include/egnn_b200.h declares, argument errors come back as status codes
 (not crashes), and the host API refuses to run without a device."""
-import ctypes as C
 import os
 import re
 

@@ -11,7 +11,7 @@ import torch
 import efficient_gnn_b200 as egnn
 from efficient_gnn_b200 import synth
 from oracle import wats_oracle as orc
-from helpers import FEATURE_CASES, elementwise_ok, elementwise_ratio, load_case, rel_max_err
+from helpers import FEATURE_CASES, elementwise_ratio, load_case, rel_max_err
 
 pytestmark = pytest.mark.gpu
 

@@ -2,7 +2,6 @@
 (the oracle would need minutes there).  For a symmetric graph L~ = L_sym - I
 has the eigenpair (-1, sqrt(w)), so T_k(L~) sqrt(w) = (-1)^k sqrt(w); the
 operator is linear and symmetric (<v, L~ x> = <L~ v, x>)."""
-import numpy as np
 import pytest
 import torch
 
