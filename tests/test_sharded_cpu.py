@@ -315,3 +315,50 @@ def test_balanced_order_fills_short_last_ranges():
                                          torch.cat([torch.arange(d) % n for d in weighted.tolist()]).int(),
                                          torch.arange(int(weighted.sum()), dtype=torch.float32))
         assert int(rp2[-1]) == int(weighted.sum()) and v2.numel() == ci2.numel()
+
+
+def _balanced_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from efficient_gnn_b200 import sharded
+        from oracle import wats_oracle as orc
+        adj = _skewed_csr(n=402, seed=11)
+        n = adj.shape[0]
+        rp = torch.from_numpy(adj.indptr.astype(np.int32))
+        ci = torch.from_numpy(adj.indices.astype(np.int32))
+        order = sharded.BalancedOrder.from_rowptr(rp, world)          # same on every rank (deterministic)
+        rp2, ci2, _ = order.relabel_csr(rp, ci)
+        part = sharded.RowPartition(n, world)
+        rpl, cil = part.slice_csr(rp2, ci2, rank)
+        sw = sharded.ShardedWavelet(rpl, cil, n, engine=NumpyEngine(), device="cpu")
+        # un-normalised combination (the F = 1 feature itself is a sign): original ids in, original order out
+        local = sw.features(k=3, s=0.8, normalize=False)
+        got = order.to_original(sw.gather_features(local))
+        want = orc.wavelet_parts(adj, k=3, s=0.8)["S"][0]
+        np.testing.assert_allclose(got.numpy(), want, atol=2e-5 * np.abs(want).max())
+        # an edge flip named by ORIGINAL node ids goes through the same map
+        u, v = 3, 250
+        val = float(1 - 2 * adj[u, v])
+        pert = adj.toarray()
+        pert[u, v] += val
+        pert[v, u] += val
+        flips = order.relabel_deltas(([u, v], [v, u], [val, val]))
+        got_d = order.to_original(sw.gather_features(sw.features(k=3, s=0.8, normalize=False, deltas=flips)))
+        want_d = orc.wavelet_parts(sp.csr_matrix(pert.astype(np.float32)), k=3, s=0.8)["S"][0]
+        np.testing.assert_allclose(got_d.numpy(), want_d, atol=2e-5 * np.abs(want_d).max())
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_balanced_renumbering_end_to_end_gloo():
+    """Skewed numbering -> BalancedOrder -> row shards over gloo -> features mapped back: equal to
+    the oracle on the ORIGINAL graph, with and without an edge flip given in original ids."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_balanced_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert [ret.get(r) for r in range(world)] == ["ok"] * world
