@@ -20,9 +20,15 @@
 //      normalisation on the last order, and the next operand dinv (.) T_k -
 //      row-sharded: stored straight into every rank's exchange window;
 //   4. grid barrier (row-sharded: one CTA then raises this rank's flag in
-//      every window).
+//      every window; before a phase stores into the windows it has seen
+//      every rank's latest flag, so no buffer is overwritten while a slower
+//      rank still stages it).
 // Results do not depend on which CTA or warp summed which slice: bitwise
 // deterministic.
+// Instantiations: PEER (exchange windows of a row-sharded graph) and PATCH
+// (UGCA recompute: the vectors passed are the base graph's, the nodes the
+// edge flips touch are re-derived in the kernel - one launch per perturbed
+// pass); the plain <false, false> one is the benchmarked default.
 #pragma once
 
 #include "common.cuh"
@@ -43,7 +49,7 @@ struct SellStepParams {
     const int32_t* slice_off;
     const int32_t* blk_slice_ptr;
     const int32_t* vslot;
-    const int32_t* cta_info;      // [n_cta] column block (-1: none), [n_cta] rank inside the block, [64] counter start
+    const int32_t* cta_info;      // [n_cta] column block (-1: none), [n_cta] rank inside the block, [64] counter start, [n_cta + 1] epilogue rows
     const int32_t* rv_ptr;
     float* vpart;
     unsigned* sched;
