@@ -180,6 +180,41 @@ def test_edge_flips_through_the_plan():
     check_parts(res, p["T"], p["S"], p["H"], "delta sell")
 
 
+def test_edge_flips_through_the_plan_with_a_callers_signal_and_an_isolating_flip():
+    """The step kernel re-derives the touched nodes' degree vectors itself (PATCH instantiation).
+    With a caller's one-column signal T_0 must stay the caller's (only dinv / iso change, and the
+    first operand dinv * T_0 is computed in the kernel); a flip that removes a node's last edge
+    must turn it into an isolated node (iso = 1, dinv = 1) for this pass only."""
+    c = load_case("cora_noloop")
+    n = c["n"]
+    dense = c["adj"].toarray()
+    deg = dense.sum(1)
+    leaf = int(np.nonzero(deg == 1)[0][0])                  # its only edge is removed below
+    nb = int(np.nonzero(dense[leaf])[0][0])
+    rows, cols, vals = [leaf, nb, 17, 2000], [nb, leaf, 2000, 17], [-1.0, -1.0, 0.0, 0.0]
+    v = float(1 - 2 * dense[17, 2000])
+    vals[2] = vals[3] = v
+    pert = dense.copy()
+    pert[leaf, nb] = pert[nb, leaf] = 0.0
+    pert[17, 2000] += v
+    pert[2000, 17] += v
+    x0 = np.random.default_rng(3).uniform(0.5, 1.5, (n, 1)).astype(np.float32)
+    g = egnn.CsrGraph.from_scipy(c["adj"])
+    assert g.sell_plan(force=True) is not None
+    base = egnn.graph_wavelet_features(g, k=3, s=[0.8, 1.6], X0=torch.from_numpy(x0), _use_sell=True, normalize=False)
+    for signal, tag in ((x0, "caller's signal"), (None, "default signal")):
+        xt = None if signal is None else torch.from_numpy(signal)
+        res = egnn.graph_wavelet_features(g, k=3, s=[0.8, 1.6], X0=xt, deltas=(rows, cols, vals), return_parts=True,
+                                          _use_sell=True)
+        p = orc.wavelet_parts(sp.csr_matrix(pert.astype(np.float32)), k=3, s=[0.8, 1.6], x0=signal)
+        check_parts(res, p["T"], p["S"], p["H"], f"delta sell, {tag}")
+        fused = egnn.graph_wavelet_features(g, k=3, s=[0.8, 1.6], X0=xt, deltas=(rows, cols, vals), _use_sell=True)
+        assert torch.allclose(fused, res.features, rtol=0, atol=1e-6)      # normalisation fused into the last order
+    # the graph itself is untouched by the perturbed passes
+    again = egnn.graph_wavelet_features(g, k=3, s=[0.8, 1.6], X0=torch.from_numpy(x0), _use_sell=True, normalize=False)
+    assert torch.equal(base, again)
+
+
 def test_unsorted_or_weighted_graphs_fall_back_to_the_csr_kernel():
     c = load_case("cora_noloop")
     a = c["adj"].tocsr()
